@@ -1,0 +1,154 @@
+/*
+ * tsplat -- C ABI of the B200-native SPH projection path (drop-in for topsy's wgpu render passes).
+ *
+ * The reference (pynbody/topsy 0.8.1) has no FFI for this path: its boundary is the Python classes
+ * SPH / RGBSPH / DepthSPH (src/topsy/sph.py), ParticleBuffers (src/topsy/particle_buffers.py) and the colormap
+ * implementations (src/topsy/colormap/implementation.py), which drive wgpu.  Each entry point below names the wgpu
+ * call sequence it replaces; INTEGRATION.md shows the ctypes stub a topsy maintainer would add.
+ *
+ * Conventions: extern "C", plain pointers and sizes, no exceptions.  Every function returns 0 on success or a
+ * negative tsplat_status; tsplat_last_error() returns a thread-local message.  All device buffers (particles,
+ * image, scratch, colormap LUT, output) are owned by the caller (PyTorch tensors in the Python host layer) and only
+ * borrowed; the context owns a few KB of constants/counters.  A context is bound to one device and is not
+ * thread-safe; different contexts may be used from different threads.  `stream` is a cudaStream_t (NULL = legacy
+ * default stream); all work is enqueued asynchronously on it.
+ */
+#ifndef TSPLAT_H
+#define TSPLAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSPLAT_ABI_VERSION 1
+
+typedef struct tsplat_ctx tsplat_ctx;
+
+typedef enum {
+    TSPLAT_OK = 0,
+    TSPLAT_ERR_INVALID = -1,   /* bad argument (Python layer raises ValueError)   */
+    TSPLAT_ERR_STATE = -2,     /* call order violated (Python layer raises RuntimeError) */
+    TSPLAT_ERR_CUDA = -3,      /* CUDA runtime failure, message has the cudaError string */
+    TSPLAT_ERR_NOMEM = -4
+} tsplat_status;
+
+/* Accumulation modes = the reference's vertex/fragment entry-point pairs (src/topsy/shaders/sph.wgsl). */
+typedef enum {
+    TSPLAT_MODE_DENSITY = 0,   /* vertex_weighting/fragment_weighting with quantity == 0: 1 channel  K*m/h^2      */
+    TSPLAT_MODE_WEIGHTED = 1,  /* vertex_weighting/fragment_weighting (sph.wgsl:75-83,138-146): (K m/h^2, K m/h^2 q) */
+    TSPLAT_MODE_RGB = 2,       /* vertex_rgb/fragment_rgb (sph.wgsl:68-73,160-165): (K r/h^2, K g/h^2, K b/h^2, 1)   */
+    TSPLAT_MODE_DEPTH = 3      /* vertex_depth/fragment_weighting (sph.wgsl:85-91): (K m/h^2, K m/h^2 z_clip)        */
+} tsplat_mode;
+
+/* channels accumulated per pixel for a mode: 1, 2, 4, 2 */
+int tsplat_mode_channels(int mode);
+
+typedef enum {
+    TSPLAT_FMT_RGBA8 = 0,      /* rgba8unorm canvas (visualizer.py:170-181)  */
+    TSPLAT_FMT_RGBA16F = 1,    /* rgba16float canvas of the 'rgb-hdr' mode   */
+    TSPLAT_FMT_RGBA32F = 2     /* Colormap.sph_raw_output_to_image float path (implementation.py:143-148) */
+} tsplat_format;
+
+typedef enum {
+    TSPLAT_CMAP_DENSITY = 0,        /* fragment_main, DENSITY        (colormap.wgsl:109-127) */
+    TSPLAT_CMAP_WEIGHTED = 1,       /* fragment_main, WEIGHTED_MEAN                           */
+    TSPLAT_CMAP_BIVARIATE = 2,      /* fragment_main, BIVARIATE + DENSITY  (colormap.wgsl:84-107) */
+    TSPLAT_CMAP_BIVARIATE_WEIGHTED = 3,
+    TSPLAT_CMAP_RGB = 4             /* fragment_main_tri (colormap.wgsl:131-159) */
+} tsplat_cmap_kind;
+
+/* The uniform block of colormap.wgsl:1-8 (already shifted for mass_scale by the host, implementation.py:427-453),
+ * plus the preprocessor switches the reference bakes into the shader source. */
+typedef struct {
+    float vmin, vmax;
+    float density_vmin, density_vmax;
+    float window_aspect_ratio;      /* width/height of the output; 1 for get_sph_presentation_image */
+    float gamma;
+    int32_t kind;                   /* tsplat_cmap_kind */
+    int32_t log_scale;              /* LOG_SCALE */
+} tsplat_colormap_params;
+
+typedef struct {
+    int64_t particles_submitted;    /* particles inside the submitted ranges since the last clear           */
+    int64_t particles_culled;       /* dropped by the z clip (0 <= z_clip <= 1) or non-positive smoothing     */
+    int64_t particles_direct;       /* splatted by the per-particle atomic path                                */
+    int64_t particles_tiled;        /* deferred to the tile-gather path                                        */
+    int64_t particles_huge;         /* deferred to the cooperative atomic path (footprint or pair overflow)    */
+    int64_t tile_pairs;             /* (particle, tile) pairs processed by the gather path                     */
+    int64_t kernel_launches;        /* CUDA kernels launched by this context since creation                    */
+} tsplat_stats;
+
+const char *tsplat_last_error(void);
+int tsplat_abi_version(void);
+
+/* Replaces: device.create_texture(rg32float/rgba32float render target) + pipeline/bind-group setup
+ * (sph.py:50-88,156-259).  `resolution` is the square render resolution R. */
+int tsplat_create(int device_ordinal, int resolution, tsplat_ctx **out);
+int tsplat_destroy(tsplat_ctx *ctx);
+
+/* Replaces SPH._setup_kernel_texture (sph.py:396-426): 5440 host floats = levels 64^2,32^2,16^2,8^2 row-major. */
+int tsplat_set_kernel_lut(tsplat_ctx *ctx, const float *host_lut, int n_floats);
+
+/* Replaces SPH._update_transform_buffer (sph.py:262-299).  M is the ROW-major 4x4 float32 matrix
+ * clipdisp @ (R/scale (+) 1) @ translate(offset), i.e. the transpose of what the reference uploads for WGSL;
+ * scale_factor = 1/scale. */
+int tsplat_set_camera(tsplat_ctx *ctx, const float *M16, float scale_factor);
+
+/* Replaces set_vertex_buffer(0, pos_smooth) (particle_buffers.py:62-68) -- device SoA float32, borrowed. */
+int tsplat_set_particles(tsplat_ctx *ctx, const float *x, const float *y, const float *z, const float *h, int64_t n);
+
+/* Replaces set_vertex_buffer(1, mass_and_quantity | rgb).  DENSITY/DEPTH: w0=m.  WEIGHTED: w0=m,w1=q.
+ * RGB: w0,w1,w2 = r,g,b.  Unused pointers may be NULL. */
+int tsplat_set_weights(tsplat_ctx *ctx, const float *w0, const float *w1, const float *w2);
+
+/* Render target: caller-owned device buffer of R*R*channels float32, pixel-interleaved, row 0 = top (+y). */
+int tsplat_set_image(tsplat_ctx *ctx, float *image, int channels);
+
+/* Caller-owned device scratch for the deferred (large-footprint) particle queue and tile bins.
+ * tsplat_scratch_bytes() gives the size needed to defer up to max_particles_per_call particles. */
+int64_t tsplat_scratch_bytes(int resolution, int64_t max_particles_per_call);
+int tsplat_set_scratch(tsplat_ctx *ctx, void *scratch, int64_t bytes);
+
+/* Replaces ParticleBuffers.update_particle_ranges + multi_draw_indirect + queue.submit of one render pass
+ * (particle_buffers.py:70-82, sph.py:318-326,337-362).  starts/lens are HOST arrays of n_ranges global particle
+ * ranges inside the current particle buffers (n_ranges == 0 -> everything).  clear != 0 == LoadOp.clear. */
+int tsplat_render(tsplat_ctx *ctx, const int64_t *starts, const int64_t *lens, int n_ranges, int mode, int clear,
+                  void *stream);
+
+/* Replaces ColormapBase.encode_render_pass (implementation.py:352-367, colormap.wgsl).  lut: device float32 RGBA,
+ * lut_w x lut_h texels (lut_h == 1 for the 1-D maps; ignored for TSPLAT_CMAP_RGB).  `image`/`channels` is the
+ * accumulation image to present (pass the buffer given to tsplat_set_image, or any other R_in x R_in image).
+ * out: device buffer out_w*out_h*4 elements of out_fmt. */
+int tsplat_colormap(tsplat_ctx *ctx, const float *image, int image_res, int channels,
+                    const tsplat_colormap_params *params, const float *lut, int lut_w, int lut_h,
+                    void *out, int out_w, int out_h, int out_fmt, void *stream);
+
+/* out[i] = a[i] + b[i] * scale, used by PeriodicSPH-style accumulation and by tests (device pointers). */
+int tsplat_image_axpy(tsplat_ctx *ctx, float *dst, const float *src, float scale, int64_t n, void *stream);
+
+/* Replaces CellLayout.from_positions' numpy pipeline (cell_layout.py:87-112) for device-resident positions.
+ * pos: device N x 3 array-of-structures in `dtype_bytes` (4 or 8) precision; box_min/cell_size are passed as doubles
+ * that already hold the value numpy would compute in the position dtype.  Outputs (device): order[N] int64 = stable
+ * argsort of the cell index, lengths[nside^3] int64.  status[0] (device int32) is set to 1 if any particle falls
+ * outside [0, nside) (the reference raises ValueError, cell_layout.py:100-101).  work: device scratch of
+ * tsplat_cell_layout_work_bytes(n, nside) bytes. */
+int64_t tsplat_cell_layout_work_bytes(int64_t n, int nside);
+int tsplat_cell_layout(int device_ordinal, const void *pos, int64_t n, int dtype_bytes, double box_min,
+                       double cell_size, int nside, int64_t *order, int64_t *lengths, int32_t *status,
+                       void *work, int64_t work_bytes, void *stream);
+
+/* Host <-> device staging for the end-to-end (host buffer) path: thin cudaMemcpyAsync wrappers so the Python host
+ * layer needs no other CUDA binding.  Replaces queue.write_buffer / queue.read_texture. */
+int tsplat_memcpy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
+int tsplat_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream);
+int tsplat_stream_sync(void *stream);
+
+/* Counters (forces a stream sync on the context's last stream). */
+int tsplat_get_stats(tsplat_ctx *ctx, tsplat_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSPLAT_H */

@@ -1,0 +1,159 @@
+"""GPU parity: the CUDA splat (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerance (BASELINE.json north_star): per-pixel relative error <= 1e-4 on every accumulated channel wherever the
+oracle pixel exceeds 1e-6 of the channel's maximum.  The oracle accumulates in fp64; the GPU in fp32 atomics.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle as co
+from oracle import topsy_oracle as o
+
+REL_TOL = 1e-4
+FLOOR = 1e-6
+
+
+def assert_image_parity(gpu, ref, what="", mag=None):
+    """|gpu - ref| <= 1e-4 * mag wherever mag > 1e-6 * max(mag).  ``mag`` is the oracle image of the same particles
+    with |weights| (== ref for the positive-definite channels: density, RGB, count, depth), i.e. the plain relative
+    error of the north_star for everything except a *signed* quantity channel, where a sum that cancels has no
+    meaningful relative error and the bound is taken relative to the accumulated magnitude instead."""
+    gpu = np.asarray(gpu, np.float64)
+    assert gpu.shape == ref.shape, (gpu.shape, ref.shape)
+    mag = np.abs(ref) if mag is None else np.abs(mag)
+    for c in range(ref.shape[2]):
+        r = ref[..., c]; g = gpu[..., c]; a = mag[..., c]
+        big = a > FLOOR * a.max()
+        if big.any():
+            rel = np.abs(g[big] - r[big]) / a[big]
+            assert rel.max() <= REL_TOL, f"{what} channel {c}: max rel err {rel.max():.3e} at {np.argmax(rel)}"
+        small = ~big
+        if small.any():
+            assert np.abs(g[small] - r[small]).max() <= 2 * FLOOR * max(a.max(), 1e-300), f"{what} ch {c} floor"
+
+
+def oracle_pair(x, y, z, h, w, M, sf, R, mode, lut, ranges=None):
+    """(reference image, magnitude image) -- the latter only differs for a signed second weight."""
+    ref = co.splat(x, y, z, h, w, M, sf, R, mode, lut, ranges=ranges)
+    if mode == o.MODE_WEIGHTED and (np.asarray(w[1]) < 0).any():
+        mag = co.splat(x, y, z, h, (w[0], np.abs(w[1])), M, sf, R, mode, lut, ranges=ranges)
+    else:
+        mag = ref
+    return ref, mag
+
+
+@pytest.fixture(scope="module")
+def engine200():
+    from topsy_b200.engine import SplatEngine
+    eng = SplatEngine(200)
+    yield eng
+    eng.close()
+
+
+def _to_dev(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda() for a in arrs]
+
+
+def _weights_for(mode, fx):
+    if mode == o.MODE_RGB:
+        rgb = fx.rgb
+        return (rgb[:, 0], rgb[:, 1], rgb[:, 2])
+    if mode == o.MODE_WEIGHTED:
+        return (fx.mass, fx.quantity.astype(np.float32))
+    return (fx.mass,)
+
+
+@pytest.mark.parametrize("mode", [o.MODE_DENSITY, o.MODE_WEIGHTED, o.MODE_RGB, o.MODE_DEPTH])
+@pytest.mark.parametrize("scale,angles", [(200.0, (0.0, 0.0)), (20.0, (0.0, 0.4)), (2.0, (0.3, 0.4)), (0.3, (1.0, -0.7)),
+                                          (2000.0, (0.2, 0.1))])
+def test_gmm_fixture_parity(engine200, oracle_lut, mode, scale, angles):
+    fx = o.GMMFixture(4000)
+    ps = fx.pos_smooth()
+    rot = o.rotate(np.eye(3), *angles)
+    M = o.transform_matrix(rot, np.array([0.3, -0.2, 0.1]), scale); sf = o.scale_factor(scale)
+    w = _weights_for(mode, fx)
+    ref, mag = oracle_pair(ps[:, 0], ps[:, 1], ps[:, 2], ps[:, 3], w, M, sf, 200, mode, oracle_lut)
+    x, y, z, h = _to_dev(ps[:, 0], ps[:, 1], ps[:, 2], ps[:, 3])
+    wd = _to_dev(*w)
+    engine200.set_kernel_lut(oracle_lut)
+    engine200.set_camera(M, sf)
+    engine200.set_particles(x, y, z, h)
+    engine200.set_weights(*wd)
+    img = engine200.render(mode).cpu().numpy()
+    assert_image_parity(img, ref, f"mode {mode} scale {scale}", mag)
+    st = engine200.stats()
+    assert st["particles_submitted"] == 4000
+    upd, culled = co.count_updates(ps[:, 0], ps[:, 1], ps[:, 2], ps[:, 3], M, sf, 200)
+    assert st["particles_culled"] == culled
+
+
+def test_ranges_and_accumulate(engine200, oracle_lut):
+    """Ragged, unaligned, empty ranges; clear=False accumulates like LoadOp.load (sph.py:337-349)."""
+    rs = np.random.RandomState(5)
+    n = 10007
+    pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+    h = (0.02 * np.exp(rs.normal(size=n) * 0.8)).astype(np.float32)
+    m = rs.uniform(0.5, 1.5, n).astype(np.float32); q = rs.normal(size=n).astype(np.float32)
+    M = o.transform_matrix(o.rotate(np.eye(3), 0.5, 0.2), np.zeros(3), 1.0); sf = o.scale_factor(1.0)
+    starts = np.array([0, 5, 5, 1001, 4099, 9000, 10006], np.int64)
+    lens = np.array([3, 0, 990, 2001, 1, 1000, 1], np.int64)
+    ref, mag = oracle_pair(pos[:, 0], pos[:, 1], pos[:, 2], h, (m, q), M, sf, 200, o.MODE_WEIGHTED, oracle_lut, ranges=(starts, lens))
+    ref2, mag2 = oracle_pair(pos[:, 0], pos[:, 1], pos[:, 2], h, (m, q), M, sf, 200, o.MODE_WEIGHTED, oracle_lut,
+                             ranges=(np.array([6000], np.int64), np.array([2500], np.int64)))
+    x, y, z, hd, md, qd = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], h, m, q)
+    engine200.set_kernel_lut(oracle_lut)
+    engine200.set_camera(M, sf)
+    engine200.set_particles(x, y, z, hd)
+    engine200.set_weights(md, qd)
+    img = engine200.render(o.MODE_WEIGHTED, starts, lens).cpu().numpy()
+    assert_image_parity(img, ref, "ranges", mag)
+    assert engine200.stats()["particles_submitted"] == lens.sum()
+    img = engine200.render(o.MODE_WEIGHTED, [6000], [2500], clear=False).cpu().numpy()
+    assert_image_parity(img, ref + ref2, "accumulate", mag + mag2)
+    with pytest.raises(ValueError):
+        engine200.render(o.MODE_WEIGHTED, [10000], [8])
+
+
+def test_empty_and_degenerate(engine200, oracle_lut):
+    """Zero particles, zero / negative / NaN smoothing lengths, particles far off screen."""
+    x, y, z, h, m = _to_dev(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0))
+    engine200.set_camera(o.transform_matrix(np.eye(3), np.zeros(3), 1.0), 1.0)
+    engine200.set_particles(x, y, z, h); engine200.set_weights(m)
+    assert float(engine200.render(o.MODE_DENSITY).abs().sum()) == 0.0
+    pos = np.array([[0, 0, 0], [0.1, 0.1, 0], [0.2, 0, 0], [1e6, 0, 0], [0, -1e6, 0], [0.5, 0.5, 0.0], [0, 0, 5.0]], np.float32)
+    hh = np.array([0.0, -1.0, np.nan, 0.1, 0.1, 0.05, 0.1], np.float32)
+    mm = np.ones(len(hh), np.float32)
+    M = o.transform_matrix(np.eye(3), np.zeros(3), 1.0)
+    ref = co.splat(pos[:, 0], pos[:, 1], pos[:, 2], hh, (mm,), M, 1.0, 200, o.MODE_DENSITY, oracle_lut)
+    x, y, z, h, m = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], hh, mm)
+    engine200.set_particles(x, y, z, h); engine200.set_weights(m)
+    img = engine200.render(o.MODE_DENSITY).cpu().numpy()
+    assert np.isfinite(img).all()
+    assert_image_parity(img, ref, "degenerate")
+
+
+@pytest.mark.parametrize("mode,R,n,hscale", [(o.MODE_DENSITY, 512, 1_000_000, 0.002), (o.MODE_RGB, 1024, 2_000_000, 0.001),
+                                            (o.MODE_WEIGHTED, 256, 200_000, 0.05)])
+def test_uniform_box_parity(oracle_lut, mode, R, n, hscale):
+    """Larger seeded runs (the oracle's C/OpenMP restatement finishes in seconds)."""
+    from topsy_b200.engine import SplatEngine
+    rs = np.random.RandomState(11)
+    pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+    h = (hscale * np.exp(rs.normal(size=n) * 0.5)).astype(np.float32)
+    w = [rs.uniform(0.1, 1.0, n).astype(np.float32) for _ in range(3)]
+    w = {o.MODE_DENSITY: w[:1], o.MODE_WEIGHTED: w[:2], o.MODE_RGB: w[:3]}[mode]
+    M = o.transform_matrix(o.rotate(np.eye(3), 0.3, 0.4), np.zeros(3), 1.0); sf = o.scale_factor(1.0)
+    ref = co.splat(pos[:, 0], pos[:, 1], pos[:, 2], h, w, M, sf, R, mode, oracle_lut)
+    eng = SplatEngine(R)
+    try:
+        eng.set_kernel_lut(oracle_lut)
+        eng.set_camera(M, sf)
+        x, y, z, hd = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], h)
+        eng.set_particles(x, y, z, hd); eng.set_weights(*_to_dev(*w))
+        img = eng.render(mode).cpu().numpy()
+        assert_image_parity(img, ref, f"uniform mode {mode}")
+    finally:
+        eng.close()

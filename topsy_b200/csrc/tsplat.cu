@@ -1,0 +1,814 @@
+// tsplat.cu -- hand-written sm_100a kernels + C ABI for topsy's SPH projection hot path.
+// See include/tsplat.h for the boundary and DESIGN.md for the data layout / roofline of each kernel.
+//
+// Kernels
+//   K1  k_project_splat<MODE>   one pass over the SoA particle arrays (128-bit loads, 4 particles / thread):
+//                               rotate/project/cull, classify by projected footprint; small footprints are splatted
+//                               immediately with vector REDs (REDG.E.ADD.F32{,x2,x4}) into the L2-resident image,
+//                               larger ones are appended to a 32-byte projected-record queue.
+//   K2  k_bin_count / k_bin_scan / k_bin_fill      tile binning of the queue (16x16 pixel tiles)
+//   K3  k_tile_gather<MODE>     thread-per-pixel tiles, whole kernel LUT in shared memory, no atomics in the loop
+//   K3b k_queue_atomic<MODE>    cooperative (warp-per-particle) atomic splat for huge footprints / pair overflow
+//   K5  k_colormap              fused normalise + log/linear + LUT (1-D / 2-D) or tri-band gamma map -> RGBA8/16F/32F
+//   K4  k_cell_*                CellLayout.from_positions: cell keys + stable counting sort
+#include "tsplat_device.cuh"
+#include "../../include/tsplat.h"
+
+#include <cuda_fp16.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+using namespace tsplat;
+
+// ------------------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return set_err(TSPLAT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                           __FILE__, __LINE__);                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TILE = 16;                    // tile edge of the gather path (pixels)
+constexpr int MAX_RANGES = 1 << 16;         // ranges per render call (reference: <= n_cells = 4096 per buffer)
+constexpr int RANGE_SLOTS = 4;              // pinned staging ring for range tables
+constexpr float DIRECT_MAX_WPX = 8.0f;      // footprints up to this width are splatted by the projecting thread
+constexpr float HUGE_MIN_WPX = 256.0f;      // footprints above this go to the cooperative atomic kernel
+
+struct Counters {
+    unsigned long long submitted, culled, direct, tiled, huge, pairs;
+    unsigned int q_count;        // deferred records in the queue (this call)
+    unsigned int huge_count;     // records routed to the cooperative atomic kernel (this call)
+    unsigned int pair_total;     // (particle, tile) pairs reserved (this call)
+    unsigned int work_counter;   // persistent-kernel work ticket
+    unsigned int n_segments;     // gather work units (this call)
+    unsigned int pad;
+};
+
+struct RangeTable {              // device layout of a multi-range call
+    const int64_t *start;        // [n]
+    const int64_t *end;          // [n]
+    const int64_t *gprefix;      // [n+1] exclusive prefix of 4-particle group counts
+    int n;
+};
+
+struct tsplat_ctx {
+    int device;
+    int R;
+    float *d_lut;                // LUT_TOTAL floats
+    bool lut_set, camera_set;
+    Camera cam;
+    const float *x, *y, *z, *h;
+    int64_t n;
+    const float *w0, *w1, *w2;
+    float *image;
+    int channels;
+    void *scratch;
+    int64_t scratch_bytes;
+    Counters *d_counters;
+    // range staging
+    int64_t *h_ranges[RANGE_SLOTS];
+    int64_t *d_ranges[RANGE_SLOTS];
+    cudaEvent_t range_evt[RANGE_SLOTS];
+    int range_slot;
+    cudaStream_t last_stream;
+    int64_t launches;
+    int sm_count;
+};
+
+extern "C" const char *tsplat_last_error(void) { return g_err; }
+extern "C" int tsplat_abi_version(void) { return TSPLAT_ABI_VERSION; }
+extern "C" int tsplat_mode_channels(int mode)
+{
+    switch (mode) {
+    case TSPLAT_MODE_DENSITY: return 1;
+    case TSPLAT_MODE_WEIGHTED: return 2;
+    case TSPLAT_MODE_RGB: return 4;
+    case TSPLAT_MODE_DEPTH: return 2;
+    default: return -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// image accumulation primitives: one RED per pixel (vector REDs need sm_90+; this file is sm_100a only)
+// ------------------------------------------------------------------------------------------------------------
+template <int MODE> struct ModeTraits;
+template <> struct ModeTraits<TSPLAT_MODE_DENSITY> { static constexpr int C = 1; };
+template <> struct ModeTraits<TSPLAT_MODE_WEIGHTED> { static constexpr int C = 2; };
+template <> struct ModeTraits<TSPLAT_MODE_RGB> { static constexpr int C = 4; };
+template <> struct ModeTraits<TSPLAT_MODE_DEPTH> { static constexpr int C = 2; };
+
+// v0..v2 follow the Deferred convention; K is the kernel value.
+template <int MODE>
+__device__ __forceinline__ void red_pixel(float *__restrict__ image, size_t pix, float K, float v0, float v1, float v2)
+{
+    if (MODE == TSPLAT_MODE_DENSITY) {
+        atomicAdd(image + pix, K * v0);
+    } else if (MODE == TSPLAT_MODE_RGB) {
+        atomicAdd(reinterpret_cast<float4 *>(image) + pix, make_float4(v0 * K, v1 * K, v2 * K, 1.0f));
+    } else {  // WEIGHTED / DEPTH: (val, val * q|cz)
+        const float val = K * v0;
+        atomicAdd(reinterpret_cast<float2 *>(image) + pix, make_float2(val, val * v1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: project / cull / classify / direct splat
+// ------------------------------------------------------------------------------------------------------------
+struct ProjectArgs {
+    const float *x, *y, *z, *h, *w0, *w1, *w2;
+    Camera cam;
+    int R;
+    float *image;
+    const float *lut;            // all levels (device)
+    Deferred *queue;
+    unsigned int queue_cap;
+    Counters *counters;
+    // single range (n_ranges == 1): particles [start, end); groups [g0, g0 + n_groups)
+    int64_t start, end, g0, n_groups;
+    int64_t n_total;             // particles in the buffers (the last 4-group may be partial)
+    RangeTable table;            // used when table.n > 0
+};
+
+template <int MODE>
+__device__ __forceinline__ void splat_direct(const Proj &p, float inv, float v0, float v1, float v2,
+                                             const float *__restrict__ lut8, float *__restrict__ image, int R)
+{
+    int j0, j1, k0, k1;
+    pixel_range(p.px0, p.px1, R, j0, j1);
+    pixel_range(p.py0, p.py1, R, k0, k1);
+    for (int k = k0; k <= k1; ++k) {
+        const float fy = (float)k + 0.5f;
+        for (int j = j0; j <= j1; ++j) {
+            const float fx = (float)j + 0.5f;
+            const float K = sample_lut8(lut8, inv, p.px0, p.py1, fx, fy);
+            if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;   // adds +0: skipping is exact (RGB still counts)
+            red_pixel<MODE>(image, (size_t)k * R + j, K, v0, v1, v2);
+        }
+    }
+}
+
+// streaming 128-bit load of 4 consecutive particles of one SoA array (read once: bypass L1 allocation)
+__device__ __forceinline__ float4 ld4(const float *__restrict__ p, int64_t group)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(reinterpret_cast<const float4 *>(p) + group));
+    return r;
+}
+
+__device__ __forceinline__ float4 ld4_tail(const float *__restrict__ p, int64_t base, int64_t left)
+{
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (left > 0) r.x = p[base];
+    if (left > 1) r.y = p[base + 1];
+    if (left > 2) r.z = p[base + 2];
+    return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_project_splat(const ProjectArgs a)
+{
+    __shared__ float s_lut8[64];
+    __shared__ unsigned long long s_cnt[3];      // culled, direct, deferred
+    if (threadIdx.x < 64) s_lut8[threadIdx.x] = a.lut[lut_offset(3) + threadIdx.x];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t group, lo, hi;
+    bool active = gi < a.n_groups;
+    if (a.table.n > 0) {
+        // binary search the range that owns group ticket gi
+        int l = 0, r = a.table.n;            // invariant: gprefix[l] <= gi < gprefix[r]
+        if (active) {
+            while (r - l > 1) {
+                const int m = (l + r) >> 1;
+                if (a.table.gprefix[m] <= gi) l = m; else r = m;
+            }
+            lo = a.table.start[l];
+            hi = a.table.end[l];
+            group = (lo >> 2) + (gi - a.table.gprefix[l]);
+        }
+    } else {
+        lo = a.start; hi = a.end; group = a.g0 + gi;
+    }
+
+    unsigned n_culled = 0, n_direct = 0, n_deferred = 0;
+    if (active) {
+        const int64_t base = group << 2;
+        float4 X, Y, Z, H, W0, W1 = make_float4(0.f, 0.f, 0.f, 0.f), W2 = W1;
+        if (base + 4 <= a.n_total) {
+            X = ld4(a.x, group); Y = ld4(a.y, group); Z = ld4(a.z, group); H = ld4(a.h, group); W0 = ld4(a.w0, group);
+            if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4(a.w1, group);
+            if (MODE == TSPLAT_MODE_RGB) W2 = ld4(a.w2, group);
+        } else {                                  // partial last group of the buffer: element-wise, in bounds
+            const int64_t left = a.n_total - base;
+            X = ld4_tail(a.x, base, left); Y = ld4_tail(a.y, base, left); Z = ld4_tail(a.z, base, left);
+            H = ld4_tail(a.h, base, left); W0 = ld4_tail(a.w0, base, left);
+            if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4_tail(a.w1, base, left);
+            if (MODE == TSPLAT_MODE_RGB) W2 = ld4_tail(a.w2, base, left);
+        }
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+        const float hs[4] = {H.x, H.y, H.z, H.w}, w0s[4] = {W0.x, W0.y, W0.z, W0.w};
+        const float w1s[4] = {W1.x, W1.y, W1.z, W1.w}, w2s[4] = {W2.x, W2.y, W2.z, W2.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = base + e;
+            if (i < lo || i >= hi) continue;
+            const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
+            if (!p.keep) { ++n_culled; continue; }
+            // entirely off-screen quads produce no fragments
+            if (!(p.px1 > 0.0f && p.px0 < a.cam.R && p.py1 > 0.0f && p.py0 < a.cam.R)) { ++n_direct; continue; }
+            const float hh = hs[e] * hs[e];
+            float v0 = w0s[e] / hh, v1, v2 = 0.0f;
+            if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] / hh; v2 = w2s[e] / hh; }
+            else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
+            else v1 = w1s[e];
+            if (p.wpx <= DIRECT_MAX_WPX) {
+                ++n_direct;
+                splat_direct<MODE>(p, 1.0f / p.wpx, v0, v1, v2, s_lut8, a.image, a.R);
+            } else {
+                ++n_deferred;
+                const unsigned slot = atomicAdd(&a.counters->q_count, 1u);
+                if (slot < a.queue_cap) {
+                    float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
+                    q[0] = make_float4(p.px0, p.px1, p.py0, p.py1);
+                    q[1] = make_float4(p.wpx, v0, v1, v2);
+                }
+            }
+        }
+    }
+    // block-aggregated statistics (3 shared + 3 global atomics per CTA)
+    if (n_culled) atomicAdd(&s_cnt[0], (unsigned long long)n_culled);
+    if (n_direct) atomicAdd(&s_cnt[1], (unsigned long long)n_direct);
+    if (n_deferred) atomicAdd(&s_cnt[2], (unsigned long long)n_deferred);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(&a.counters->culled, s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&a.counters->direct, s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&a.counters->huge, s_cnt[2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3b: cooperative atomic splat of queue records (one warp per record, lanes along pixel rows)
+// ------------------------------------------------------------------------------------------------------------
+struct QueueArgs {
+    const Deferred *queue;
+    const unsigned int *indices;     // optional indirection (huge list); nullptr -> identity
+    const unsigned int *count;       // device pointer to the number of entries
+    unsigned int cap;
+    const float *lut;
+    float *image;
+    int R;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_queue_atomic(const QueueArgs a)
+{
+    __shared__ float s_lut[LUT_TOTAL];
+    for (int i = threadIdx.x; i < LUT_TOTAL; i += blockDim.x) s_lut[i] = a.lut[i];
+    __syncthreads();
+    const unsigned count = min(*a.count, a.cap);
+    const int lane = threadIdx.x & 31;
+    const unsigned warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += warps_per_grid) {
+        const unsigned idx = a.indices ? a.indices[w] : w;
+        const float4 q0 = reinterpret_cast<const float4 *>(a.queue + idx)[0];
+        const float4 q1 = reinterpret_cast<const float4 *>(a.queue + idx)[1];
+        const float px0 = q0.x, px1 = q0.y, py0 = q0.z, py1 = q0.w, wpx = q1.x;
+        const float inv = 1.0f / wpx;
+        int j0, j1, k0, k1;
+        pixel_range(px0, px1, a.R, j0, j1);
+        pixel_range(py0, py1, a.R, k0, k1);
+        for (int k = k0; k <= k1; ++k) {
+            const float fy = (float)k + 0.5f;
+            for (int j = j0 + lane; j <= j1; j += 32) {
+                const float fx = (float)j + 0.5f;
+                const float K = sample_lut(s_lut, wpx, inv, px0, py1, fx, fy);
+                if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;
+                red_pixel<MODE>(a.image, (size_t)k * a.R + j, K, q1.y, q1.z, q1.w);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: fused normalise + log/linear + colormap LUT  (colormap.wgsl:75-159)
+// ------------------------------------------------------------------------------------------------------------
+struct CmapArgs {
+    const float *image;
+    int res, channels;
+    tsplat_colormap_params p;
+    const float *lut;
+    int lut_w, lut_h;
+    void *out;
+    int out_w, out_h, out_fmt;
+};
+
+__device__ __forceinline__ float wgsl_log10(float v) { return logf(v) / 2.30258509f; }
+
+__device__ __forceinline__ float clamp01(float t) { return fminf(fmaxf(t, 0.0f), 1.0f); }   // NaN -> 0
+
+__device__ __forceinline__ float4 lut_fetch(const float *__restrict__ lut, int idx)
+{
+    return __ldg(reinterpret_cast<const float4 *>(lut) + idx);
+}
+
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t)
+{
+    return make_float4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t);
+}
+
+// linear-filtered, clamp-to-edge fetch at normalised coordinate t (texel centres at (i + 0.5)/n)
+__device__ __forceinline__ float4 lut_sample_1d(const float *__restrict__ lut, int n, float t)
+{
+    const float p = t * (float)n - 0.5f;
+    const float i0 = floorf(p);
+    const float f = p - i0;
+    const int a = min(max((int)i0, 0), n - 1), b = min(max((int)i0 + 1, 0), n - 1);
+    return lerp4(lut_fetch(lut, a), lut_fetch(lut, b), f);
+}
+
+__device__ __forceinline__ float4 lut_sample_2d(const float *__restrict__ lut, int nx, int ny, float tx, float ty)
+{
+    const float px = tx * (float)nx - 0.5f, py = ty * (float)ny - 0.5f;
+    const float ix = floorf(px), iy = floorf(py);
+    const float fx = px - ix, fy = py - iy;
+    const int x0 = min(max((int)ix, 0), nx - 1), x1 = min(max((int)ix + 1, 0), nx - 1);
+    const int y0 = min(max((int)iy, 0), ny - 1), y1 = min(max((int)iy + 1, 0), ny - 1);
+    const float4 top = lerp4(lut_fetch(lut, y0 * nx + x0), lut_fetch(lut, y0 * nx + x1), fx);
+    const float4 bot = lerp4(lut_fetch(lut, y1 * nx + x0), lut_fetch(lut, y1 * nx + x1), fx);
+    return lerp4(top, bot, fy);
+}
+
+__device__ __forceinline__ void load_pixel(const float *__restrict__ img, int res, int C, int col, int row, float v[4])
+{
+    const size_t pix = (size_t)row * res + col;
+    if (C == 1) { v[0] = img[pix]; v[1] = 0.f; v[2] = 0.f; v[3] = 0.f; }
+    else if (C == 2) { const float2 t = reinterpret_cast<const float2 *>(img)[pix]; v[0] = t.x; v[1] = t.y; v[2] = 0.f; v[3] = 0.f; }
+    else { const float4 t = reinterpret_cast<const float4 *>(img)[pix]; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+}
+
+__global__ void __launch_bounds__(256) k_colormap(const CmapArgs a)
+{
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y;
+    if (ox >= a.out_w || oy >= a.out_h) return;
+    float v[4];
+    if (a.out_w == a.res && a.out_h == a.res) {
+        load_pixel(a.image, a.res, a.channels, ox, oy, v);       // texel centres coincide with pixel centres
+    } else {
+        // vertex_main (colormap.wgsl:41-73): the square image covers the larger window dimension
+        const float asp = a.p.window_aspect_ratio;
+        const float sx = asp > 1.0f ? 1.0f : 1.0f / asp, sy = asp > 1.0f ? asp : 1.0f;
+        const float X = -1.0f + (2.0f * ox + 1.0f) / (float)a.out_w;
+        const float Y = 1.0f - (2.0f * oy + 1.0f) / (float)a.out_h;
+        const float u = clamp01((X / sx + 1.0f) * 0.5f), w = clamp01((1.0f - Y / sy) * 0.5f);
+        const float texels_per_px = (float)a.res / fmaxf((float)a.out_w, (float)a.out_h);
+        if (texels_per_px <= 1.0f) {        // magnification: linear filter (implementation.py:278-279)
+            const float px = u * a.res - 0.5f, py = w * a.res - 0.5f;
+            const float ix = floorf(px), iy = floorf(py);
+            const float fx = px - ix, fy = py - iy;
+            const int x0 = min(max((int)ix, 0), a.res - 1), x1 = min(max((int)ix + 1, 0), a.res - 1);
+            const int y0 = min(max((int)iy, 0), a.res - 1), y1 = min(max((int)iy + 1, 0), a.res - 1);
+            float t00[4], t01[4], t10[4], t11[4];
+            load_pixel(a.image, a.res, a.channels, x0, y0, t00);
+            load_pixel(a.image, a.res, a.channels, x1, y0, t01);
+            load_pixel(a.image, a.res, a.channels, x0, y1, t10);
+            load_pixel(a.image, a.res, a.channels, x1, y1, t11);
+            for (int c = 0; c < 4; ++c) {
+                const float top = t00[c] + (t01[c] - t00[c]) * fx, bot = t10[c] + (t11[c] - t10[c]) * fx;
+                v[c] = top + (bot - top) * fy;
+            }
+        } else {                            // minification: nearest (WebGPU default min_filter)
+            const int x = min(max((int)floorf(u * a.res), 0), a.res - 1);
+            const int y = min(max((int)floorf(w * a.res), 0), a.res - 1);
+            load_pixel(a.image, a.res, a.channels, x, y, v);
+        }
+    }
+
+    float4 rgba;
+    const tsplat_colormap_params &p = a.p;
+    if (p.kind == TSPLAT_CMAP_RGB) {
+        float c3[3] = {v[0], v[1], v[2]};
+        for (int c = 0; c < 3; ++c) {
+            float val = c3[c];
+            if (p.log_scale) val = wgsl_log10(val);
+            const float t = fmaxf((val - p.vmin) / (p.vmax - p.vmin), 0.0f);
+            c3[c] = powf(t, p.gamma);
+        }
+        rgba = make_float4(c3[0], c3[1], c3[2], 1.0f);
+    } else {
+        const bool weighted = (p.kind == TSPLAT_CMAP_WEIGHTED || p.kind == TSPLAT_CMAP_BIVARIATE_WEIGHTED);
+        float val = weighted ? v[1] / v[0] : v[0];
+        if (p.log_scale) val = wgsl_log10(val);
+        const float t = clamp01((val - p.vmin) / (p.vmax - p.vmin));
+        if (p.kind == TSPLAT_CMAP_BIVARIATE || p.kind == TSPLAT_CMAP_BIVARIATE_WEIGHTED) {
+            const float d = clamp01((wgsl_log10(v[0]) - p.density_vmin) / (p.density_vmax - p.density_vmin));
+            rgba = lut_sample_2d(a.lut, a.lut_w, a.lut_h, d, t);
+        } else {
+            rgba = lut_sample_1d(a.lut, a.lut_w, t);
+        }
+    }
+
+    const size_t o = (size_t)oy * a.out_w + ox;
+    if (a.out_fmt == TSPLAT_FMT_RGBA8) {
+        uchar4 q;
+        q.x = (unsigned char)__float2int_rn(__saturatef(rgba.x) * 255.0f);
+        q.y = (unsigned char)__float2int_rn(__saturatef(rgba.y) * 255.0f);
+        q.z = (unsigned char)__float2int_rn(__saturatef(rgba.z) * 255.0f);
+        q.w = (unsigned char)__float2int_rn(__saturatef(rgba.w) * 255.0f);
+        reinterpret_cast<uchar4 *>(a.out)[o] = q;
+    } else if (a.out_fmt == TSPLAT_FMT_RGBA16F) {
+        __half2 lo = __floats2half2_rn(rgba.x, rgba.y), hi = __floats2half2_rn(rgba.z, rgba.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned int *>(&lo);
+        pk.y = *reinterpret_cast<unsigned int *>(&hi);
+        reinterpret_cast<uint2 *>(a.out)[o] = pk;
+    } else {
+        reinterpret_cast<float4 *>(a.out)[o] = rgba;
+    }
+}
+
+__global__ void k_axpy(float *__restrict__ dst, const float *__restrict__ src, float scale, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = dst[i] + src[i] * scale;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int tsplat_create(int device_ordinal, int resolution, tsplat_ctx **out)
+{
+    if (!out) return set_err(TSPLAT_ERR_INVALID, "out is NULL");
+    if (resolution <= 0 || resolution > 32768) return set_err(TSPLAT_ERR_INVALID, "bad resolution %d", resolution);
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    tsplat_ctx *c = new (std::nothrow) tsplat_ctx();
+    if (!c) return set_err(TSPLAT_ERR_NOMEM, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->device = device_ordinal;
+    c->R = resolution;
+    c->cam.R = (float)resolution;
+    c->cam.halfR = 0.5f * (float)resolution;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaMalloc(&c->d_lut, LUT_TOTAL * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(Counters)));
+    CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(Counters)));
+    for (int s = 0; s < RANGE_SLOTS; ++s) {
+        CUDA_TRY(cudaMallocHost(&c->h_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
+        CUDA_TRY(cudaMalloc(&c->d_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->range_evt[s], cudaEventDisableTiming));
+    }
+    *out = c;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_destroy(tsplat_ctx *c)
+{
+    if (!c) return TSPLAT_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_lut);
+    cudaFree(c->d_counters);
+    for (int s = 0; s < RANGE_SLOTS; ++s) {
+        cudaFreeHost(c->h_ranges[s]);
+        cudaFree(c->d_ranges[s]);
+        cudaEventDestroy(c->range_evt[s]);
+    }
+    delete c;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_set_kernel_lut(tsplat_ctx *c, const float *host_lut, int n_floats)
+{
+    if (!c || !host_lut) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (n_floats != LUT_TOTAL) return set_err(TSPLAT_ERR_INVALID, "kernel LUT must have %d floats, got %d", LUT_TOTAL, n_floats);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpy(c->d_lut, host_lut, LUT_TOTAL * sizeof(float), cudaMemcpyHostToDevice));
+    c->lut_set = true;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_set_camera(tsplat_ctx *c, const float *M16, float scale_factor)
+{
+    if (!c || !M16) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 12; ++i) c->cam.m[i] = M16[i];
+    c->cam.sf = scale_factor;
+    c->camera_set = true;
+    return TSPLAT_OK;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int tsplat_set_particles(tsplat_ctx *c, const float *x, const float *y, const float *z, const float *h, int64_t n)
+{
+    if (!c) return set_err(TSPLAT_ERR_INVALID, "NULL context");
+    if (n < 0 || n >= ((int64_t)1 << 33)) return set_err(TSPLAT_ERR_INVALID, "bad particle count %lld", (long long)n);
+    if (n > 0 && (!x || !y || !z || !h)) return set_err(TSPLAT_ERR_INVALID, "NULL particle array");
+    if (!aligned16(x) || !aligned16(y) || !aligned16(z) || !aligned16(h))
+        return set_err(TSPLAT_ERR_INVALID, "particle arrays must be 16-byte aligned (128-bit loads)");
+    c->x = x; c->y = y; c->z = z; c->h = h; c->n = n;
+    c->w0 = c->w1 = c->w2 = nullptr;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_set_weights(tsplat_ctx *c, const float *w0, const float *w1, const float *w2)
+{
+    if (!c) return set_err(TSPLAT_ERR_INVALID, "NULL context");
+    if (!aligned16(w0) || !aligned16(w1) || !aligned16(w2))
+        return set_err(TSPLAT_ERR_INVALID, "weight arrays must be 16-byte aligned (128-bit loads)");
+    c->w0 = w0; c->w1 = w1; c->w2 = w2;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_set_image(tsplat_ctx *c, float *image, int channels)
+{
+    if (!c || !image) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (channels != 1 && channels != 2 && channels != 4) return set_err(TSPLAT_ERR_INVALID, "channels must be 1, 2 or 4");
+    if (!aligned16(image)) return set_err(TSPLAT_ERR_INVALID, "image must be 16-byte aligned");
+    c->image = image; c->channels = channels;
+    return TSPLAT_OK;
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct ScratchLayout {
+    int64_t queue_off, queue_cap;          // Deferred records
+    int64_t total;
+};
+
+static ScratchLayout scratch_layout(int R, int64_t bytes_or_particles, bool from_bytes)
+{
+    (void)R;
+    ScratchLayout L;
+    L.queue_off = 0;
+    if (from_bytes) {
+        L.queue_cap = bytes_or_particles / (int64_t)sizeof(Deferred);
+    } else {
+        L.queue_cap = bytes_or_particles;
+    }
+    if (L.queue_cap > 0xffffff00ll) L.queue_cap = 0xffffff00ll;
+    L.total = align_up(L.queue_cap * (int64_t)sizeof(Deferred), 256);
+    return L;
+}
+
+extern "C" int64_t tsplat_scratch_bytes(int resolution, int64_t max_particles_per_call)
+{
+    if (max_particles_per_call < 0) return -1;
+    return scratch_layout(resolution, max_particles_per_call, false).total;
+}
+
+extern "C" int tsplat_set_scratch(tsplat_ctx *c, void *scratch, int64_t bytes)
+{
+    if (!c) return set_err(TSPLAT_ERR_INVALID, "NULL context");
+    if (bytes < 0 || (bytes > 0 && !scratch)) return set_err(TSPLAT_ERR_INVALID, "bad scratch");
+    if (!aligned16(scratch)) return set_err(TSPLAT_ERR_INVALID, "scratch must be 16-byte aligned");
+    c->scratch = scratch; c->scratch_bytes = bytes;
+    return TSPLAT_OK;
+}
+
+template <int MODE>
+static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups, cudaStream_t st)
+{
+    const int threads = 256;
+    const int64_t blocks = (n_groups + threads - 1) / threads;
+    if (blocks > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
+    if (blocks > 0) {
+        k_project_splat<MODE><<<(unsigned)blocks, threads, 0, st>>>(pa);
+        c->launches++;
+    }
+    QueueArgs qa;
+    qa.queue = pa.queue; qa.indices = nullptr; qa.count = &c->d_counters->q_count; qa.cap = pa.queue_cap;
+    qa.lut = c->d_lut; qa.image = c->image; qa.R = c->R;
+    if (pa.queue_cap > 0) {
+        k_queue_atomic<MODE><<<c->sm_count * 8, 256, 0, st>>>(qa);
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t *lens, int n_ranges, int mode,
+                             int clear, void *stream)
+{
+    if (!c) return set_err(TSPLAT_ERR_INVALID, "NULL context");
+    const int C = tsplat_mode_channels(mode);
+    if (C < 0) return set_err(TSPLAT_ERR_INVALID, "unknown mode %d", mode);
+    if (!c->lut_set) return set_err(TSPLAT_ERR_STATE, "kernel LUT not set");
+    if (!c->camera_set) return set_err(TSPLAT_ERR_STATE, "camera not set");
+    if (!c->image) return set_err(TSPLAT_ERR_STATE, "image not set");
+    if (c->channels != C) return set_err(TSPLAT_ERR_INVALID, "mode %d needs a %d-channel image, have %d", mode, C, c->channels);
+    if (c->n > 0 && !c->x) return set_err(TSPLAT_ERR_STATE, "particles not set");
+    if (c->n > 0 && !c->w0) return set_err(TSPLAT_ERR_STATE, "weights not set");
+    if ((mode == TSPLAT_MODE_WEIGHTED || mode == TSPLAT_MODE_RGB) && c->n > 0 && !c->w1)
+        return set_err(TSPLAT_ERR_STATE, "second weight array not set");
+    if (mode == TSPLAT_MODE_RGB && c->n > 0 && !c->w2) return set_err(TSPLAT_ERR_STATE, "third weight array not set");
+    if (n_ranges < 0 || n_ranges > MAX_RANGES) return set_err(TSPLAT_ERR_INVALID, "n_ranges %d out of [0, %d]", n_ranges, MAX_RANGES);
+    if (n_ranges > 0 && (!starts || !lens)) return set_err(TSPLAT_ERR_INVALID, "NULL range arrays");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->last_stream = st;
+
+    if (clear) {
+        CUDA_TRY(cudaMemsetAsync(c->image, 0, sizeof(float) * (size_t)c->R * c->R * C, st));
+        CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), st));
+    }
+    const ScratchLayout L = scratch_layout(c->R, c->scratch_bytes, true);
+
+    // validate + count
+    int64_t one_start = 0, one_len = c->n;
+    if (n_ranges == 0) { starts = &one_start; lens = &one_len; n_ranges = 1; }
+    int64_t total = 0, total_groups = 0;
+    for (int r = 0; r < n_ranges; ++r) {
+        if (starts[r] < 0 || lens[r] < 0 || starts[r] + lens[r] > c->n)
+            return set_err(TSPLAT_ERR_INVALID, "range %d = [%lld, +%lld) outside the %lld particles of the buffer", r,
+                           (long long)starts[r], (long long)lens[r], (long long)c->n);
+        total += lens[r];
+        if (lens[r] > 0) total_groups += ((starts[r] + lens[r] + 3) >> 2) - (starts[r] >> 2);
+    }
+    if (total == 0) return TSPLAT_OK;
+    if (L.queue_cap < total && L.queue_cap < (int64_t)1 << 20)
+        return set_err(TSPLAT_ERR_STATE, "scratch too small: need tsplat_scratch_bytes(R, >= min(particles per call, 2^20))");
+
+    ProjectArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.x = c->x; pa.y = c->y; pa.z = c->z; pa.h = c->h; pa.w0 = c->w0; pa.w1 = c->w1; pa.w2 = c->w2;
+    pa.cam = c->cam; pa.R = c->R; pa.image = c->image; pa.lut = c->d_lut;
+    pa.queue = reinterpret_cast<Deferred *>(static_cast<char *>(c->scratch) + L.queue_off);
+    pa.counters = c->d_counters;
+    pa.n_total = c->n;
+
+    // Each launch may defer at most queue_cap particles: split the call into chunks of <= queue_cap particles.
+    // (With scratch sized by tsplat_scratch_bytes(R, max block) this is a single chunk.)
+    const int64_t chunk_cap = L.queue_cap;
+    int rc = TSPLAT_OK;
+    auto submit = [&](const ProjectArgs &args, int64_t n_groups, int64_t n_particles) -> int {
+        CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, 6 * sizeof(unsigned int), st));
+        ProjectArgs a2 = args;
+        a2.queue_cap = (unsigned)(chunk_cap < n_particles ? chunk_cap : n_particles);
+        a2.n_groups = n_groups;
+        switch (mode) {
+        case TSPLAT_MODE_DENSITY: return launch_render<TSPLAT_MODE_DENSITY>(c, a2, n_groups, st);
+        case TSPLAT_MODE_WEIGHTED: return launch_render<TSPLAT_MODE_WEIGHTED>(c, a2, n_groups, st);
+        case TSPLAT_MODE_RGB: return launch_render<TSPLAT_MODE_RGB>(c, a2, n_groups, st);
+        default: return launch_render<TSPLAT_MODE_DEPTH>(c, a2, n_groups, st);
+        }
+    };
+
+    if (n_ranges == 1 || total <= 0) {
+        // single range: split by chunk_cap particles
+        int64_t s = starts[0];
+        const int64_t e = starts[0] + lens[0];
+        while (s < e) {
+            const int64_t ce = (e - s > chunk_cap) ? s + chunk_cap : e;
+            pa.start = s; pa.end = ce; pa.g0 = s >> 2;
+            const int64_t ng = ((ce + 3) >> 2) - (s >> 2);
+            pa.table.n = 0;
+            rc = submit(pa, ng, ce - s);
+            if (rc) return rc;
+            s = ce;
+        }
+    } else {
+        // multi-range: stage (start, end, gprefix) through a pinned ring slot; chunk by cumulative particle count
+        int r0 = 0;
+        while (r0 < n_ranges) {
+            const int slot = c->range_slot;
+            c->range_slot = (c->range_slot + 1) % RANGE_SLOTS;
+            CUDA_TRY(cudaEventSynchronize(c->range_evt[slot]));     // previous use of this slot has been copied
+            int64_t *hs = c->h_ranges[slot];
+            int64_t acc = 0, groups = 0;
+            int r1 = r0, m = 0;
+            // layout: start[m] | end[m] | gprefix[m+1]  (m known only at the end -> use MAX stride of this chunk)
+            const int cap_m = n_ranges - r0;
+            int64_t *h_start = hs, *h_end = hs + cap_m, *h_pref = hs + 2 * (int64_t)cap_m;
+            while (r1 < n_ranges) {
+                const int64_t len = lens[r1];
+                if (len > chunk_cap) return set_err(TSPLAT_ERR_STATE, "a single range exceeds the scratch capacity");
+                if (acc + len > chunk_cap && m > 0) break;
+                if (len > 0) {
+                    h_start[m] = starts[r1]; h_end[m] = starts[r1] + len; h_pref[m] = groups;
+                    groups += ((starts[r1] + len + 3) >> 2) - (starts[r1] >> 2);
+                    ++m;
+                }
+                acc += len;
+                ++r1;
+            }
+            h_pref[m] = groups;
+            if (m > 0) {
+                int64_t *ds = c->d_ranges[slot];
+                CUDA_TRY(cudaMemcpyAsync(ds, hs, sizeof(int64_t) * (3 * (size_t)cap_m + 1), cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaEventRecord(c->range_evt[slot], st));
+                pa.table.start = ds; pa.table.end = ds + cap_m; pa.table.gprefix = ds + 2 * (int64_t)cap_m; pa.table.n = m;
+                rc = submit(pa, groups, acc);
+                if (rc) return rc;
+            }
+            r0 = r1;
+        }
+    }
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_colormap(tsplat_ctx *c, const float *image, int image_res, int channels,
+                               const tsplat_colormap_params *params, const float *lut, int lut_w, int lut_h,
+                               void *out, int out_w, int out_h, int out_fmt, void *stream)
+{
+    if (!c || !image || !params || !out) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (channels != 1 && channels != 2 && channels != 4) return set_err(TSPLAT_ERR_INVALID, "channels must be 1, 2 or 4");
+    if (image_res <= 0 || out_w <= 0 || out_h <= 0) return set_err(TSPLAT_ERR_INVALID, "bad size");
+    if (out_fmt < TSPLAT_FMT_RGBA8 || out_fmt > TSPLAT_FMT_RGBA32F) return set_err(TSPLAT_ERR_INVALID, "bad output format");
+    const int kind = params->kind;
+    if (kind < TSPLAT_CMAP_DENSITY || kind > TSPLAT_CMAP_RGB) return set_err(TSPLAT_ERR_INVALID, "bad colormap kind");
+    if (kind == TSPLAT_CMAP_RGB && channels < 4) return set_err(TSPLAT_ERR_INVALID, "RGB map needs a 4-channel image");
+    if ((kind == TSPLAT_CMAP_WEIGHTED || kind == TSPLAT_CMAP_BIVARIATE_WEIGHTED) && channels < 2)
+        return set_err(TSPLAT_ERR_INVALID, "weighted map needs a 2-channel image");
+    if (kind != TSPLAT_CMAP_RGB) {
+        if (!lut || lut_w <= 0 || lut_h <= 0) return set_err(TSPLAT_ERR_INVALID, "colormap LUT missing");
+        if (!aligned16(lut)) return set_err(TSPLAT_ERR_INVALID, "colormap LUT must be 16-byte aligned");
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CmapArgs a;
+    a.image = image; a.res = image_res; a.channels = channels; a.p = *params;
+    a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_w = out_w; a.out_h = out_h; a.out_fmt = out_fmt;
+    dim3 grid((out_w + 255) / 256, out_h);
+    k_colormap<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    c->launches++;
+    c->last_stream = (cudaStream_t)stream;
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_image_axpy(tsplat_ctx *c, float *dst, const float *src, float scale, int64_t n, void *stream)
+{
+    if (!c || !dst || !src || n < 0) return set_err(TSPLAT_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return TSPLAT_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > c->sm_count * 32) blocks = c->sm_count * 32;
+    k_axpy<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, scale, n);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_memcpy_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst_dev || !src_host))) return set_err(TSPLAT_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_memcpy_d2h(void *dst_host, const void *src_dev, int64_t bytes, void *stream)
+{
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_dev))) return set_err(TSPLAT_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_stream_sync(void *stream)
+{
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_get_stats(tsplat_ctx *c, tsplat_stats *out)
+{
+    if (!c || !out) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Counters h;
+    CUDA_TRY(cudaStreamSynchronize(c->last_stream));
+    CUDA_TRY(cudaMemcpy(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out->particles_culled = (int64_t)h.culled;
+    out->particles_direct = (int64_t)h.direct;
+    out->particles_tiled = (int64_t)h.tiled;
+    out->particles_huge = (int64_t)h.huge;
+    out->tile_pairs = (int64_t)h.pairs;
+    out->particles_submitted = (int64_t)(h.culled + h.direct + h.tiled + h.huge);
+    out->kernel_launches = c->launches;
+    return TSPLAT_OK;
+}
+
+// cell layout entry points are in tsplat_cells.cu
