@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark of the SPH projection hot path: Gparticles/s splatted and ms/frame.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1..c5] [--impl ours|reference]
+
+A "step" is one full frame of the hot path over one synthetic snapshot: camera upload -> splat every particle
+(EXPORT-style blocks) -> [N>1: sum-reduce of the partial images over NVLink] -> fused normalise/log/colormap -> RGBA
+on the device.  Prints ONE JSON line (see the repository's DESIGN.md section 7 for every field).
+
+`--impl reference`: the reference's GPU implementation (wgpu) and pynbody's CPU renderer cannot be installed in this
+image (no wheels, no network), so the reference arm times the CPU restatement of the same path (oracle/splat_oracle.c,
+fp32 accumulators, all host cores) on a bounded sample of the same workload -- kind "port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Gparticles/s splatted"
+UNIT = "Gparticles/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=None, help="override particles per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+def camera_for(workload):
+    from topsy_b200 import camera
+    rot = camera.rotate(np.eye(3), *workload.rotate)
+    return camera.transform_matrix(rot, np.zeros(3), workload.scale), np.float32(1.0 / workload.scale)
+
+
+MODE_ID = {"density": 0, "weighted": 1, "rgb": 2}
+
+
+def export_blocks(n, block=2 ** 25):
+    """EXPORT-frame blocks of RenderProgression.get_block (progressive_render.py:55-64)."""
+    return [(s, min(block, n - s)) for s in range(0, n, block)]
+
+
+def footprint_stats(h, workload):
+    w = 2.0 * h * workload.resolution / workload.scale
+    qs = np.quantile(w, [0.5, 0.99])
+    return {"median_px": float(qs[0]), "p99_px": float(qs[1])}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(workload, host, n_sample, repeats=1):
+    """Times oracle/splat_oracle.c (fp32 accumulators, all cores) on the first n_sample particles."""
+    from oracle import c_oracle as co
+    from oracle import topsy_oracle as o
+    from topsy_b200 import synthetic
+    M, sf = camera_for(workload)
+    lut = o.kernel_lut()
+    names = synthetic.weight_names(workload.mode)
+    arrs = [host[k][:n_sample] for k in ("x", "y", "z", "h")]
+    w = [host[k][:n_sample] for k in names]
+    mode = MODE_ID[workload.mode]
+    R = workload.resolution
+    img = np.zeros((R, R, co.MODE_CHANNELS[mode]), np.float32)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        co.splat(*arrs, w, M, sf, R, mode, lut, out=img, clear=True, accum=np.float32)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_sample / best / 1e9, best, co.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from topsy_b200 import synthetic
+    wl = synthetic.WORKLOADS[args.workload]
+    n_total = wl.n_particles * args.gpus
+    # bounded sample: calibrate on 2e5 particles, then size each step to ~3 s of CPU work
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    n_gen = min(wl.n_particles if args.particles is None else args.particles, 20_000_000)
+    data = synthetic.generate(wl, dev, n_total=n_total, n=n_gen)
+    host = {k: v.cpu().numpy() for k, v in data.items()}
+    del data
+    rate0, _, cores = cpu_port_rate(wl, host, min(200_000, n_gen))
+    n_sample = int(min(n_gen, max(200_000, rate0 * 1e9 * 3.0)))
+    for _ in range(args.warmup):
+        cpu_port_rate(wl, host, n_sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_rate(wl, host, n_sample)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = n_sample / dt / 1e9
+    cpu_name = ""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                cpu_name = ln.split(":", 1)[1].strip(); break
+    except Exception:
+        pass
+    sample = f"first {n_sample} particles of workload {wl.name} ({wl.description}) per step, full {wl.resolution}^2 image"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl.name}: {wl.description}", "resolution": wl.resolution, "mode": wl.mode,
+                       "particles_per_step": n_sample, "note": "wgpu/pynbody not installable here: CPU restatement "
+                       "(oracle/splat_oracle.c, OpenMP, fp32 accumulators) of the reference path"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "cpu": cpu_name, "os_cpu_count": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from topsy_b200 import synthetic, _native as N
+    from topsy_b200.engine import SplatEngine
+    from topsy_b200.colormap import luts
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = synthetic.WORKLOADS[args.workload]
+    n = wl.n_particles if args.particles is None else args.particles
+    n_total = n * world
+    R = wl.resolution
+    mode = MODE_ID[wl.mode]
+    C = N.MODE_CHANNELS[mode]
+    data = synthetic.generate(wl, dev, n_total=n_total, rank=rank, n=n)
+    names = synthetic.weight_names(wl.mode)
+    M, sf = camera_for(wl)
+
+    eng = SplatEngine(R, device=local_rank)
+    eng.set_camera(M, sf)
+    eng.set_particles(data["x"], data["y"], data["z"], data["h"])
+    eng.set_weights(*[data[k] for k in names])
+    blocks = export_blocks(n)
+    img = eng.image(C)
+    out = torch.empty((R, R, 4), dtype=torch.uint8, device=dev)
+
+    # colormap stage: rgb -> tri-band log/gamma map; density/weighted -> log10 + 1-D LUT (implementation.py)
+    params = N.ColormapParams()
+    params.window_aspect_ratio = 1.0; params.gamma = 1.0; params.log_scale = 1
+    params.density_vmin = 0.0; params.density_vmax = 1.0
+    if wl.mode == "rgb":
+        params.kind = N.CMAP_RGB; lut = None
+    else:
+        params.kind = N.CMAP_WEIGHTED if wl.mode == "weighted" else N.CMAP_DENSITY
+        lut = torch.from_numpy(luts.colormap_table_1d("twilight_shifted", 1000)).to(dev)
+
+    def frame(ev=None):
+        for bi, (s, l) in enumerate(blocks):
+            eng.render(mode, [s], [l], clear=(bi == 0))
+        if ev is not None:
+            ev[0].record()
+        if world > 1:
+            dist.all_reduce(img, op=dist.ReduceOp.SUM)
+        if ev is not None:
+            ev[1].record()
+        eng.colormap(img, params, lut, out, N.FMT_RGBA8)
+
+    # one untimed frame to fix vmin/vmax from the image (autorange percentiles, implementation.py:381-425,512-531)
+    frame()
+    torch.cuda.synchronize()
+    ch = img[..., :3] if wl.mode == "rgb" else (img[..., 1] / img[..., 0] if wl.mode == "weighted" else img[..., 0])
+    v = torch.log10(ch[ch > 0].flatten().float())
+    if v.numel() > 200:
+        sub = v[torch.randint(0, v.numel(), (min(v.numel(), 2_000_000),), device=dev)]
+        vmax = float(torch.quantile(sub, 0.999)); vmin = float(torch.quantile(sub, 0.01))
+        if wl.mode == "rgb":
+            vmin = vmax - 3.0
+    else:
+        vmin, vmax = 0.0, 1.0
+    params.vmin, params.vmax = vmin, vmax
+
+    for _ in range(args.warmup):
+        frame()
+    launches0 = eng.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        evs[k][0].record()
+        frame(ev=(evs[k][1], evs[k][2]))
+        evs[k][3].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    st = eng.stats()
+    launches = st["kernel_launches"] - launches0
+    total_ms = evs[0][0].elapsed_time(evs[-1][3])
+    splat_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    reduce_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    cmap_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    t = torch.tensor([total_ms, splat_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, splat_ms_max = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end-to-end: host buffers in, RGBA image out, copies inside the timed region -------------------------
+    e2e = None
+    if not args.no_e2e:
+        keys = ["x", "y", "z", "h"] + list(names)
+        host = {k: torch.empty(n, dtype=torch.float32, pin_memory=True) for k in keys}
+        for k in keys:
+            host[k].copy_(data[k])
+        host_out = torch.empty((R, R, 4), dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        h2d = sum(host[k].numel() * 4 for k in keys)
+        d2h = host_out.numel()
+
+        def e2e_frame():
+            for k in keys:
+                eng.upload(data[k], host[k])
+            frame()
+            eng.download(host_out, out)
+            eng.synchronize()
+
+        n_e2e = max(2, min(args.steps, 5))
+        e2e_frame()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_frame()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        e2e = {"value": n_total / dt / 1e9, "unit": UNIT, "ms_per_frame": dt * 1e3, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "frames": n_e2e,
+               "path": "pinned host SoA -> tsplat_memcpy_h2d -> tsplat_render -> tsplat_colormap -> tsplat_memcpy_d2h"}
+        del host
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bytes_alg = n * wl.bytes_per_particle          # per GPU, per frame: compulsory particle reads of the splat pass
+        achieved = bytes_alg / (splat_ms_max * 1e-3) / 1e9
+        h_cpu = data["h"][: min(n, 2_000_000)].cpu().numpy()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl.name}: {wl.description}", "particles_per_gpu": n, "particles_total": n_total,
+                       "resolution": R, "mode": wl.mode, "channels": C, "scale": wl.scale, "rotate": list(wl.rotate),
+                       "generator": "uniform box, lognormal h (topsy_b200/synthetic.py)", "h_factor": wl.h_factor,
+                       "footprint_px": footprint_stats(h_cpu, wl), "blocks_per_frame": len(blocks),
+                       "l2_policy": "inputs (%.2f GB per frame) exceed the 126 MB L2; no flush needed" % (bytes_alg / 1e9),
+                       "parallelism": f"particle shards x{world}, image all-reduce" if world > 1 else "single GPU"},
+            "phases_ms": {"splat": splat_ms_max, "reduce": reduce_ms, "colormap": cmap_ms},
+            "roofline": {"bound": "hbm", "kernel": "k_project_splat (+ deferred queue kernels) per frame",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_frame": bytes_alg, "traffic": None,
+                         "bytes_per_particle": wl.bytes_per_particle},
+            "gpu_launches": int(launches),
+            "stats": {k: int(v) for k, v in st.items()},
+            "wall_ms_per_step": t_wall * 1e3 / args.steps,
+            "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            n_c = min(n, 4_000_000)
+            host_np = {k: data[k][:n_c].cpu().numpy() for k in ["x", "y", "z", "h"] + list(names)}
+            r0, _, cores = cpu_port_rate(wl, host_np, min(200_000, n_c))
+            n_s = int(min(n_c, max(200_000, r0 * 1e9 * 5.0)))
+            rate, secs, cores = cpu_port_rate(wl, host_np, n_s, repeats=3)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {n_s} particles of the same workload, best of 3 ({secs:.2f} s each), "
+                                              f"oracle/splat_oracle.c with fp32 accumulators",
+                                    "os_cpu_count": os.cpu_count()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

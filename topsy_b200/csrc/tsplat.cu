@@ -149,24 +149,6 @@ struct ProjectArgs {
     RangeTable table;            // used when table.n > 0
 };
 
-template <int MODE>
-__device__ __forceinline__ void splat_direct(const Proj &p, float inv, float v0, float v1, float v2,
-                                             const float *__restrict__ lut8, float *__restrict__ image, int R)
-{
-    int j0, j1, k0, k1;
-    pixel_range(p.px0, p.px1, R, j0, j1);
-    pixel_range(p.py0, p.py1, R, k0, k1);
-    for (int k = k0; k <= k1; ++k) {
-        const float fy = (float)k + 0.5f;
-        for (int j = j0; j <= j1; ++j) {
-            const float fx = (float)j + 0.5f;
-            const float K = sample_lut8(lut8, inv, p.px0, p.py1, fx, fy);
-            if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;   // adds +0: skipping is exact (RGB still counts)
-            red_pixel<MODE>(image, (size_t)k * R + j, K, v0, v1, v2);
-        }
-    }
-}
-
 // streaming 128-bit load of 4 consecutive particles of one SoA array (read once: bypass L1 allocation)
 __device__ __forceinline__ float4 ld4(const float *__restrict__ p, int64_t group)
 {
@@ -185,22 +167,49 @@ __device__ __forceinline__ float4 ld4_tail(const float *__restrict__ p, int64_t 
     return r;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256) k_project_splat(const ProjectArgs a)
+// K1 works in two phases per warp so that the accumulation phase is divergence-free:
+//   phase A  every lane projects its 4 particles; small-footprint ones become 48-byte records in the warp's slice of
+//            shared memory, with the exclusive prefix of their "cell" counts; a bit vector marks segment heads.
+//   phase B  the warp walks the flattened (particle, cell) list 32 entries at a time; a cell is the group of CELL_W
+//            horizontally adjacent pixels that one 128-bit vector RED covers:
+//               RGB      4 channels -> 1 pixel     WEIGHTED/DEPTH 2 channels -> 2 pixels     DENSITY 1 channel -> 4 pixels
+constexpr int K1_THREADS = 128;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_RECS = 128;                 // records per warp batch (4 per lane)
+constexpr int K1_MAX_SPAN = 8;               // direct particles cover at most 8 x 8 pixel centres
+constexpr int K1_BITWORDS = K1_RECS * K1_MAX_SPAN * K1_MAX_SPAN / 32;
+
+struct __align__(16) DirectRec {
+    float px0, py1, inv, v0;
+    float v1, v2;
+    unsigned cjk;        // first cell column (low 16) | first row k0 (high 16)
+    unsigned jj;         // first covered pixel column j0 (low 16) | last j1 (high 16)
+    unsigned off;        // offset of the particle's first cell in the warp's flattened list
+    unsigned ncj;        // cell columns
+    unsigned magic;      // ceil(65536 / ncj): (t * magic) >> 16 == t / ncj for t < 4096
+    unsigned pad;
+};
+
+template <int MODE, int CELL_W>
+__global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs a)
 {
+    constexpr int CELL_SHIFT = CELL_W == 4 ? 2 : CELL_W == 2 ? 1 : 0;
     __shared__ float s_lut8[64];
-    __shared__ unsigned long long s_cnt[3];      // culled, direct, deferred
+    __shared__ DirectRec s_rec[K1_WARPS][K1_RECS];
+    __shared__ unsigned s_bits[K1_WARPS][K1_BITWORDS];
+    __shared__ unsigned s_cnt[3];                // culled, direct, deferred (this CTA)
     if (threadIdx.x < 64) s_lut8[threadIdx.x] = a.lut[lut_offset(3) + threadIdx.x];
-    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t group, lo, hi;
-    bool active = gi < a.n_groups;
-    if (a.table.n > 0) {
-        // binary search the range that owns group ticket gi
-        int l = 0, r = a.table.n;            // invariant: gprefix[l] <= gi < gprefix[r]
-        if (active) {
+    int64_t group = 0, lo = 0, hi = 0;
+    const bool active = gi < a.n_groups;
+    if (active) {
+        if (a.table.n > 0) {
+            int l = 0, r = a.table.n;            // invariant: gprefix[l] <= gi < gprefix[r]
             while (r - l > 1) {
                 const int m = (l + r) >> 1;
                 if (a.table.gprefix[m] <= gi) l = m; else r = m;
@@ -208,65 +217,172 @@ __global__ void __launch_bounds__(256) k_project_splat(const ProjectArgs a)
             lo = a.table.start[l];
             hi = a.table.end[l];
             group = (lo >> 2) + (gi - a.table.gprefix[l]);
+        } else {
+            lo = a.start; hi = a.end; group = a.g0 + gi;
         }
-    } else {
-        lo = a.start; hi = a.end; group = a.g0 + gi;
+    }
+
+    // ---- phase A: load, project, classify ---------------------------------------------------------------
+    float xs[4], ys[4], zs[4], hs[4], w0s[4], w1s[4], w2s[4];
+    {
+        float4 X, Y, Z, H, W0, W1, W2;
+        X = Y = Z = H = W0 = W1 = W2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t base = group << 2;
+        if (active) {
+            if (base + 4 <= a.n_total) {
+                X = ld4(a.x, group); Y = ld4(a.y, group); Z = ld4(a.z, group); H = ld4(a.h, group); W0 = ld4(a.w0, group);
+                if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4(a.w1, group);
+                if (MODE == TSPLAT_MODE_RGB) W2 = ld4(a.w2, group);
+            } else {                              // partial last group of the buffer: element-wise, in bounds
+                const int64_t left = a.n_total - base;
+                X = ld4_tail(a.x, base, left); Y = ld4_tail(a.y, base, left); Z = ld4_tail(a.z, base, left);
+                H = ld4_tail(a.h, base, left); W0 = ld4_tail(a.w0, base, left);
+                if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4_tail(a.w1, base, left);
+                if (MODE == TSPLAT_MODE_RGB) W2 = ld4_tail(a.w2, base, left);
+            }
+        }
+        xs[0] = X.x; xs[1] = X.y; xs[2] = X.z; xs[3] = X.w;   ys[0] = Y.x; ys[1] = Y.y; ys[2] = Y.z; ys[3] = Y.w;
+        zs[0] = Z.x; zs[1] = Z.y; zs[2] = Z.z; zs[3] = Z.w;   hs[0] = H.x; hs[1] = H.y; hs[2] = H.z; hs[3] = H.w;
+        w0s[0] = W0.x; w0s[1] = W0.y; w0s[2] = W0.z; w0s[3] = W0.w;
+        w1s[0] = W1.x; w1s[1] = W1.y; w1s[2] = W1.z; w1s[3] = W1.w;
+        w2s[0] = W2.x; w2s[1] = W2.y; w2s[2] = W2.z; w2s[3] = W2.w;
     }
 
     unsigned n_culled = 0, n_direct = 0, n_deferred = 0;
-    if (active) {
-        const int64_t base = group << 2;
-        float4 X, Y, Z, H, W0, W1 = make_float4(0.f, 0.f, 0.f, 0.f), W2 = W1;
-        if (base + 4 <= a.n_total) {
-            X = ld4(a.x, group); Y = ld4(a.y, group); Z = ld4(a.z, group); H = ld4(a.h, group); W0 = ld4(a.w0, group);
-            if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4(a.w1, group);
-            if (MODE == TSPLAT_MODE_RGB) W2 = ld4(a.w2, group);
-        } else {                                  // partial last group of the buffer: element-wise, in bounds
-            const int64_t left = a.n_total - base;
-            X = ld4_tail(a.x, base, left); Y = ld4_tail(a.y, base, left); Z = ld4_tail(a.z, base, left);
-            H = ld4_tail(a.h, base, left); W0 = ld4_tail(a.w0, base, left);
-            if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4_tail(a.w1, base, left);
-            if (MODE == TSPLAT_MODE_RGB) W2 = ld4_tail(a.w2, base, left);
-        }
-        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-        const float hs[4] = {H.x, H.y, H.z, H.w}, w0s[4] = {W0.x, W0.y, W0.z, W0.w};
-        const float w1s[4] = {W1.x, W1.y, W1.z, W1.w}, w2s[4] = {W2.x, W2.y, W2.z, W2.w};
+    unsigned run_cells = 0, run_recs = 0;         // warp-uniform running totals
+    unsigned head_off[4];
+    bool has_rec[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int64_t i = base + e;
-            if (i < lo || i >= hi) continue;
+    for (int e = 0; e < 4; ++e) {
+        const int64_t i = (group << 2) + e;
+        unsigned cells = 0;
+        DirectRec rec;
+        if (active && i >= lo && i < hi) {
             const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
-            if (!p.keep) { ++n_culled; continue; }
-            // entirely off-screen quads produce no fragments
-            if (!(p.px1 > 0.0f && p.px0 < a.cam.R && p.py1 > 0.0f && p.py0 < a.cam.R)) { ++n_direct; continue; }
-            const float hh = hs[e] * hs[e];
-            float v0 = w0s[e] / hh, v1, v2 = 0.0f;
-            if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] / hh; v2 = w2s[e] / hh; }
-            else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
-            else v1 = w1s[e];
-            if (p.wpx <= DIRECT_MAX_WPX) {
-                ++n_direct;
-                splat_direct<MODE>(p, 1.0f / p.wpx, v0, v1, v2, s_lut8, a.image, a.R);
+            if (!p.keep) {
+                ++n_culled;
             } else {
-                ++n_deferred;
-                const unsigned slot = atomicAdd(&a.counters->q_count, 1u);
-                if (slot < a.queue_cap) {
-                    float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
-                    q[0] = make_float4(p.px0, p.px1, p.py0, p.py1);
-                    q[1] = make_float4(p.wpx, v0, v1, v2);
+                int j0, j1, k0, k1;
+                pixel_range(p.px0, p.px1, a.R, j0, j1);
+                pixel_range(p.py0, p.py1, a.R, k0, k1);
+                if (j1 < j0 || k1 < k0) {
+                    ++n_direct;                   // no pixel centre covered (sub-pixel or off-screen): nothing to add
+                } else {
+                    const float hh = hs[e] * hs[e];
+                    const float v0 = w0s[e] / hh;
+                    float v1, v2 = 0.0f;
+                    if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] / hh; v2 = w2s[e] / hh; }
+                    else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
+                    else v1 = w1s[e];
+                    if (p.wpx <= DIRECT_MAX_WPX && j1 - j0 < K1_MAX_SPAN && k1 - k0 < K1_MAX_SPAN) {
+                        ++n_direct;
+                        const int cj0 = j0 >> CELL_SHIFT, cj1 = j1 >> CELL_SHIFT;
+                        const unsigned ncj = (unsigned)(cj1 - cj0 + 1);
+                        cells = ncj * (unsigned)(k1 - k0 + 1);
+                        rec.px0 = p.px0; rec.py1 = p.py1; rec.inv = 1.0f / p.wpx;
+                        rec.v0 = v0; rec.v1 = v1; rec.v2 = v2;
+                        rec.cjk = (unsigned)cj0 | ((unsigned)k0 << 16);
+                        rec.jj = (unsigned)j0 | ((unsigned)j1 << 16);
+                        rec.ncj = ncj;
+                        rec.magic = (65536u + ncj - 1u) / ncj;
+                        rec.pad = 0u;
+                    } else {
+                        ++n_deferred;
+                        const unsigned slot = atomicAdd(&a.counters->q_count, 1u);
+                        if (slot < a.queue_cap) {
+                            float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
+                            q[0] = make_float4(p.px0, p.px1, p.py0, p.py1);
+                            q[1] = make_float4(p.wpx, v0, v1, v2);
+                        }
+                    }
+                }
+            }
+        }
+        // warp-wide exclusive prefix of the cell counts, compaction rank of the records
+        unsigned incl = cells;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned have = __ballot_sync(0xffffffffu, cells > 0);
+        has_rec[e] = cells > 0;
+        head_off[e] = run_cells + incl - cells;
+        if (cells > 0) {
+            rec.off = head_off[e];
+            s_rec[warp][run_recs + __popc(have & lt_mask)] = rec;
+        }
+        run_cells += total;
+        run_recs += __popc(have);
+    }
+
+    // ---- phase B: flattened (particle, cell) list ------------------------------------------------------------
+    const unsigned T = run_cells;
+    const unsigned n_words = (T + 31u) >> 5;
+    for (unsigned wi = lane; wi < n_words; wi += 32) s_bits[warp][wi] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (has_rec[e]) atomicOr(&s_bits[warp][head_off[e] >> 5], 1u << (head_off[e] & 31u));
+    __syncwarp();
+
+    unsigned rec_base = 0;
+    for (unsigned wi = 0; wi < n_words; ++wi) {
+        const unsigned word = s_bits[warp][wi];
+        const unsigned t = (wi << 5) + lane;
+        const unsigned ridx = rec_base + __popc(word & (lt_mask | (1u << lane))) - 1u;
+        rec_base += __popc(word);
+        if (t < T) {
+            const DirectRec &r = s_rec[warp][ridx];
+            const float4 ra = *reinterpret_cast<const float4 *>(&r.px0);      // px0 py1 inv v0
+            const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk jj
+            const uint4 rc = *reinterpret_cast<const uint4 *>(&r.off);        // off ncj magic pad
+            const unsigned cjk = __float_as_uint(rb.z), jj = __float_as_uint(rb.w);
+            const unsigned local = t - rc.x;
+            const unsigned dk = (local * rc.z) >> 16;
+            const unsigned dc = local - dk * rc.y;
+            const int k = (int)(cjk >> 16) + (int)dk;
+            const int cj = (int)(cjk & 0xffffu) + (int)dc;
+            const int j0 = (int)(jj & 0xffffu), j1 = (int)(jj >> 16);
+            const float fy = (float)k + 0.5f;
+            if (CELL_W == 1) {
+                const float K = sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)cj + 0.5f, fy);
+                if (MODE == TSPLAT_MODE_RGB || K != 0.0f)            // adding +0 is a no-op; RGB still counts fragments
+                    red_pixel<MODE>(a.image, (size_t)k * a.R + cj, K, ra.w, rb.x, rb.y);
+            } else {
+                float Ks[CELL_W];
+                bool any = false;
+#pragma unroll
+                for (int c = 0; c < CELL_W; ++c) {
+                    const int j = cj * CELL_W + c;
+                    const bool in = (j >= j0) && (j <= j1);
+                    Ks[c] = in ? sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)j + 0.5f, fy) : 0.0f;
+                    any |= (Ks[c] != 0.0f);
+                }
+                if (any) {
+                    const size_t pix = (size_t)k * a.R + (size_t)cj * CELL_W;
+                    if (MODE == TSPLAT_MODE_DENSITY) {
+                        atomicAdd(reinterpret_cast<float4 *>(a.image + pix),
+                                  make_float4(Ks[0] * ra.w, Ks[1] * ra.w, Ks[2 % CELL_W] * ra.w, Ks[3 % CELL_W] * ra.w));
+                    } else {                                  // two pixels x (val, val * q|cz)
+                        const float a0 = Ks[0] * ra.w, a1 = Ks[1] * ra.w;
+                        atomicAdd(reinterpret_cast<float4 *>(a.image + 2 * pix), make_float4(a0, a0 * rb.x, a1, a1 * rb.x));
+                    }
                 }
             }
         }
     }
-    // block-aggregated statistics (3 shared + 3 global atomics per CTA)
-    if (n_culled) atomicAdd(&s_cnt[0], (unsigned long long)n_culled);
-    if (n_direct) atomicAdd(&s_cnt[1], (unsigned long long)n_direct);
-    if (n_deferred) atomicAdd(&s_cnt[2], (unsigned long long)n_deferred);
+
+    // block-aggregated statistics
+    if (n_culled) atomicAdd(&s_cnt[0], n_culled);
+    if (n_direct) atomicAdd(&s_cnt[1], n_direct);
+    if (n_deferred) atomicAdd(&s_cnt[2], n_deferred);
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (s_cnt[0]) atomicAdd(&a.counters->culled, s_cnt[0]);
-        if (s_cnt[1]) atomicAdd(&a.counters->direct, s_cnt[1]);
-        if (s_cnt[2]) atomicAdd(&a.counters->huge, s_cnt[2]);
+        if (s_cnt[0]) atomicAdd(&a.counters->culled, (unsigned long long)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&a.counters->direct, (unsigned long long)s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&a.counters->huge, (unsigned long long)s_cnt[2]);
     }
 }
 
@@ -594,11 +710,14 @@ extern "C" int tsplat_set_scratch(tsplat_ctx *c, void *scratch, int64_t bytes)
 template <int MODE>
 static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups, cudaStream_t st)
 {
-    const int threads = 256;
+    const int threads = K1_THREADS;
     const int64_t blocks = (n_groups + threads - 1) / threads;
     if (blocks > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
     if (blocks > 0) {
-        k_project_splat<MODE><<<(unsigned)blocks, threads, 0, st>>>(pa);
+        // cell width of the vector REDs: as many pixels as fit 128 bits, if rows keep the cells aligned
+        constexpr int CW = ModeTraits<MODE>::C == 1 ? 4 : ModeTraits<MODE>::C == 2 ? 2 : 1;
+        if (CW > 1 && (c->R % CW) == 0) k_project_splat<MODE, CW><<<(unsigned)blocks, threads, 0, st>>>(pa);
+        else k_project_splat<MODE, 1><<<(unsigned)blocks, threads, 0, st>>>(pa);
         c->launches++;
     }
     QueueArgs qa;
