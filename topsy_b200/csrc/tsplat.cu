@@ -93,6 +93,7 @@ struct tsplat_ctx {
     cudaStream_t last_stream;
     int64_t launches;
     int sm_count;
+    bool bin_attr_set;
 };
 
 extern "C" const char *tsplat_last_error(void) { return g_err; }
@@ -382,7 +383,6 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     if (threadIdx.x == 0) {
         if (s_cnt[0]) atomicAdd(&a.counters->culled, (unsigned long long)s_cnt[0]);
         if (s_cnt[1]) atomicAdd(&a.counters->direct, (unsigned long long)s_cnt[1]);
-        if (s_cnt[2]) atomicAdd(&a.counters->huge, (unsigned long long)s_cnt[2]);
     }
 }
 
@@ -403,12 +403,12 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_queue_atomic(const QueueArgs a)
 {
     __shared__ float s_lut[LUT_TOTAL];
+    const unsigned count = min(*a.count, a.cap);
+    if (blockIdx.x >= count) return;
     for (int i = threadIdx.x; i < LUT_TOTAL; i += blockDim.x) s_lut[i] = a.lut[i];
     __syncthreads();
-    const unsigned count = min(*a.count, a.cap);
-    const int lane = threadIdx.x & 31;
-    const unsigned warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += warps_per_grid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned w = blockIdx.x; w < count; w += gridDim.x) {
         const unsigned idx = a.indices ? a.indices[w] : w;
         const float4 q0 = reinterpret_cast<const float4 *>(a.queue + idx)[0];
         const float4 q1 = reinterpret_cast<const float4 *>(a.queue + idx)[1];
@@ -417,13 +417,366 @@ __global__ void __launch_bounds__(256) k_queue_atomic(const QueueArgs a)
         int j0, j1, k0, k1;
         pixel_range(px0, px1, a.R, j0, j1);
         pixel_range(py0, py1, a.R, k0, k1);
-        for (int k = k0; k <= k1; ++k) {
+        for (int k = k0 + warp; k <= k1; k += 8) {
             const float fy = (float)k + 0.5f;
             for (int j = j0 + lane; j <= j1; j += 32) {
                 const float fx = (float)j + 0.5f;
                 const float K = sample_lut(s_lut, wpx, inv, px0, py1, fx, fy);
                 if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;
                 red_pixel<MODE>(a.image, (size_t)k * a.R + j, K, q1.y, q1.z, q1.w);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2: tile binning of the deferred queue (counting sort by 16x16-pixel tile, all on the device)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SEG = 512;                      // pairs per gather work unit
+constexpr unsigned ROUTE_TILED = 1, ROUTE_HUGE = 2;
+
+struct BinArgs {
+    const Deferred *queue;
+    unsigned queue_cap;
+    Counters *counters;
+    unsigned char *route;            // [queue_cap]
+    unsigned int *huge_idx;          // [queue_cap]
+    unsigned int *tile_count;        // [nt]
+    unsigned int *tile_offset;       // [nt + 1]
+    unsigned int *tile_cursor;       // [nt]
+    unsigned int *seg_prefix;        // [nt + 1]
+    unsigned int *seg_tile;          // [seg_cap] tile of each gather work unit
+    unsigned int seg_cap;
+    unsigned int *pairs;             // [pairs_cap]
+    unsigned int pairs_cap;
+    int R, ntx, nt;
+};
+
+__device__ __forceinline__ void tile_range(const Deferred &d, int R, int &tx0, int &tx1, int &ty0, int &ty1)
+{
+    int j0, j1, k0, k1;
+    pixel_range(d.px0, d.px1, R, j0, j1);
+    pixel_range(d.py0, d.py1, R, k0, k1);
+    if (j1 < j0 || k1 < k0) { tx0 = ty0 = 1; tx1 = ty1 = 0; return; }
+    tx0 = j0 / TILE; tx1 = j1 / TILE; ty0 = k0 / TILE; ty1 = k1 / TILE;
+}
+
+constexpr unsigned SMALL_QUEUE = 131072;      // below this many deferred records the binning machinery is not worth it
+
+// Pass 1: route every deferred record (tile gather / cooperative atomics) and histogram the (record, tile) pairs.
+// The histogram is privatised in shared memory (native integer ATOMS) and flushed with one global RED per
+// non-empty (CTA, tile): global atomics on a few thousand hot tile counters would serialise in the L2.
+// USE_SMEM == false is the fallback for resolutions whose tile table does not fit in shared memory.
+template <bool USE_SMEM>
+__global__ void __launch_bounds__(1024) k_bin_count(const BinArgs a)
+{
+    extern __shared__ unsigned s_hist[];
+    const unsigned Q = min(a.counters->q_count, a.queue_cap);
+    if (USE_SMEM) {
+        for (int i = threadIdx.x; i < a.nt; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    const bool all_atomic = Q < SMALL_QUEUE;
+    // contiguous chunk per CTA (k_bin_fill uses the same partition)
+    const unsigned per = (Q + gridDim.x - 1) / gridDim.x;
+    const unsigned r0 = blockIdx.x * per, r1 = min(Q, r0 + per);
+    unsigned n_tiled = 0, n_huge = 0, n_pairs = 0;
+    const int lane = threadIdx.x & 31;
+    for (unsigned rb = r0 + (threadIdx.x & ~31u); rb < r1; rb += blockDim.x) {      // warp-uniform trip count
+        const unsigned r = rb + lane;
+        const bool valid = r < r1;
+        Deferred d;
+        d.wpx = 0.0f;
+        int tx0 = 1, tx1 = 0, ty0 = 1, ty1 = 0;
+        if (valid) { d = a.queue[r]; tile_range(d, a.R, tx0, tx1, ty0, ty1); }
+        const bool covers = valid && tx1 >= tx0 && ty1 >= ty0;
+        const unsigned np = covers ? (unsigned)(tx1 - tx0 + 1) * (unsigned)(ty1 - ty0 + 1) : 0u;
+        bool tiled = covers && !all_atomic && d.wpx <= HUGE_MIN_WPX;
+        // one pair-capacity reservation per warp (a same-address ATOMG per record would serialise in the L2)
+        unsigned want = tiled ? np : 0u, incl = want;
+        for (int s = 1; s < 32; s <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += t;
+        }
+        const unsigned warp_total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned base = 0;
+        if (lane == 0 && warp_total) base = atomicAdd(&a.counters->pair_total, warp_total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (tiled) {
+            const unsigned end = base + incl;
+            tiled = end <= a.pairs_cap && end >= base;
+        }
+        if (valid) {
+            unsigned route = 0;
+            if (tiled) {
+                route = ROUTE_TILED;
+                ++n_tiled; n_pairs += np;
+                for (int ty = ty0; ty <= ty1; ++ty)
+                    for (int tx = tx0; tx <= tx1; ++tx) {
+                        if (USE_SMEM) atomicAdd(&s_hist[ty * a.ntx + tx], 1u);
+                        else atomicAdd(&a.tile_count[ty * a.ntx + tx], 1u);
+                    }
+            } else if (covers) {
+                route = ROUTE_HUGE;
+                ++n_huge;
+            } else {
+                ++n_tiled;      // covers no pixel centre inside the image
+            }
+            a.route[r] = (unsigned char)route;
+        }
+        // warp-aggregated append to the cooperative-atomic list
+        const unsigned hm = __ballot_sync(0xffffffffu, valid && covers && !tiled);
+        if (hm) {
+            unsigned hb = 0;
+            if (lane == 0) hb = atomicAdd(&a.counters->huge_count, (unsigned)__popc(hm));
+            hb = __shfl_sync(0xffffffffu, hb, 0);
+            if (valid && covers && !tiled) a.huge_idx[hb + __popc(hm & ((1u << lane) - 1u))] = r;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        n_tiled += __shfl_down_sync(0xffffffffu, n_tiled, d);
+        n_huge += __shfl_down_sync(0xffffffffu, n_huge, d);
+        n_pairs += __shfl_down_sync(0xffffffffu, n_pairs, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_tiled) atomicAdd(&a.counters->tiled, (unsigned long long)n_tiled);
+        if (n_huge) atomicAdd(&a.counters->huge, (unsigned long long)n_huge);
+        if (n_pairs) atomicAdd(&a.counters->pairs, (unsigned long long)n_pairs);
+    }
+    if (USE_SMEM) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.nt; i += blockDim.x) {
+            const unsigned v = s_hist[i];
+            if (v) atomicAdd(&a.tile_count[i], v);
+        }
+    }
+}
+
+// single CTA: exclusive scans of the tile counts (pair offsets) and of the per-tile segment counts (work units),
+// plus the work-unit -> tile table the gather kernel indexes with its ticket
+__global__ void __launch_bounds__(1024) k_bin_scan(const BinArgs a)
+{
+    constexpr int PER = 8, CHUNK = 1024 * PER;
+    __shared__ unsigned s_val[CHUNK];            // tile counts of the current chunk (coalesced staging)
+    __shared__ unsigned s_cnt[1024], s_seg[1024];
+    unsigned carry_c = 0, carry_g = 0;           // running totals (identical in every thread)
+    for (int c0 = 0; c0 < a.nt; c0 += CHUNK) {
+        const int n = min(CHUNK, a.nt - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < CHUNK; i += 1024) s_val[i] = i < n ? a.tile_count[c0 + i] : 0u;
+        __syncthreads();
+        unsigned c = 0, g = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const unsigned t = s_val[threadIdx.x * PER + i];
+            c += t; g += (t + SEG - 1) / SEG;
+        }
+        s_cnt[threadIdx.x] = c; s_seg[threadIdx.x] = g;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {     // Hillis-Steele inclusive scan over the 1024 partials
+            unsigned tc = 0, tg = 0;
+            if ((int)threadIdx.x >= d) { tc = s_cnt[threadIdx.x - d]; tg = s_seg[threadIdx.x - d]; }
+            __syncthreads();
+            s_cnt[threadIdx.x] += tc; s_seg[threadIdx.x] += tg;
+            __syncthreads();
+        }
+        unsigned ec = carry_c + s_cnt[threadIdx.x] - c, eg = carry_g + s_seg[threadIdx.x] - g;     // exclusive
+        carry_c += s_cnt[1023]; carry_g += s_seg[1023];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = threadIdx.x * PER + i;
+            const unsigned t = s_val[idx];
+            const unsigned ns = (t + SEG - 1) / SEG;
+            if (idx < n) {
+                a.tile_offset[c0 + idx] = ec; a.seg_prefix[c0 + idx] = eg;
+                for (unsigned q = 0; q < ns; ++q)
+                    if (eg + q < a.seg_cap) a.seg_tile[eg + q] = (unsigned)(c0 + idx);
+            }
+            ec += t; eg += ns;
+        }
+    }
+    if (threadIdx.x == 0) {
+        a.tile_offset[a.nt] = carry_c;
+        a.seg_prefix[a.nt] = carry_g;
+        a.counters->n_segments = min(carry_g, a.seg_cap);
+        a.counters->work_counter = 0u;
+    }
+}
+
+// Pass 2: scatter record indices into their tiles.  Each CTA re-histograms its chunk in shared memory, reserves one
+// contiguous run per non-empty tile with a single global atomic, then hands out slots with shared-memory atomics.
+template <bool USE_SMEM>
+__global__ void __launch_bounds__(1024) k_bin_fill(const BinArgs a)
+{
+    extern __shared__ unsigned s_mem[];
+    unsigned *s_base = s_mem, *s_cur = s_mem + a.nt;
+    const unsigned Q = min(a.counters->q_count, a.queue_cap);
+    const unsigned per = (Q + gridDim.x - 1) / gridDim.x;
+    const unsigned r0 = blockIdx.x * per, r1 = min(Q, r0 + per);
+    if (USE_SMEM) {
+        for (int i = threadIdx.x; i < 2 * a.nt; i += blockDim.x) s_mem[i] = 0u;
+        __syncthreads();
+        for (unsigned r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+            if (a.route[r] != ROUTE_TILED) continue;
+            const Deferred d = a.queue[r];
+            int tx0, tx1, ty0, ty1;
+            tile_range(d, a.R, tx0, tx1, ty0, ty1);
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cur[ty * a.ntx + tx], 1u);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.nt; i += blockDim.x) {
+            const unsigned v = s_cur[i];
+            if (v) s_base[i] = a.tile_offset[i] + atomicAdd(&a.tile_cursor[i], v);
+            s_cur[i] = 0u;
+        }
+        __syncthreads();
+    }
+    for (unsigned r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        if (a.route[r] != ROUTE_TILED) continue;
+        const Deferred d = a.queue[r];
+        int tx0, tx1, ty0, ty1;
+        tile_range(d, a.R, tx0, tx1, ty0, ty1);
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const int t = ty * a.ntx + tx;
+                if (USE_SMEM) a.pairs[s_base[t] + atomicAdd(&s_cur[t], 1u)] = r;
+                else a.pairs[a.tile_offset[t] + atomicAdd(&a.tile_cursor[t], 1u)] = r;
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3: tile gather -- one thread per pixel of a 16x16 tile, registers accumulate, no atomics inside the loop
+// ------------------------------------------------------------------------------------------------------------
+struct GatherArgs {
+    const Deferred *queue;
+    const unsigned int *pairs;
+    const unsigned int *tile_offset;
+    const unsigned int *seg_prefix;
+    const unsigned int *seg_tile;
+    Counters *counters;
+    const float *lut;
+    float *image;
+    int R, ntx, nt;
+};
+
+// same arithmetic as sample_lut(), with the per-record level decode hoisted: nf = texels per side (float),
+// code = lut offset | (bilinear << 31)
+__device__ __forceinline__ float sample_lut_pre(const float *__restrict__ lut, float inv, float nf, unsigned code,
+                                                float px0, float py1, float fx, float fy)
+{
+    const float u = (fx - px0) * inv;
+    const float v = (py1 - fy) * inv;
+    if (code & 0x80000000u) {
+        const float tu = fmaf(u, 64.0f, -0.5f), tv = fmaf(v, 64.0f, -0.5f);
+        const float iu = floorf(tu), iv = floorf(tv);
+        const float fu = tu - iu, fv = tv - iv;
+        const int a = (int)iu, b = (int)iv;
+        const int a0 = min(max(a, 0), 63), a1 = min(max(a + 1, 0), 63);
+        const int b0 = min(max(b, 0), 63), b1 = min(max(b + 1, 0), 63);
+        const float t00 = lut[b0 * 64 + a0], t01 = lut[b0 * 64 + a1];
+        const float t10 = lut[b1 * 64 + a0], t11 = lut[b1 * 64 + a1];
+        const float top = fmaf(fu, t01 - t00, t00);
+        const float bot = fmaf(fu, t11 - t10, t10);
+        return fmaf(fv, bot - top, top);
+    }
+    const int n = (int)nf;
+    const int iu = min(max(__float2int_rd(u * nf), 0), n - 1);
+    const int iv = min(max(__float2int_rd(v * nf), 0), n - 1);
+    return lut[(code & 0x7fffffffu) + iv * n + iu];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
+{
+    constexpr int C = ModeTraits<MODE>::C;
+    __shared__ float s_lut[LUT_TOTAL];
+    __shared__ float4 s_a[256];          // px0 px1 py0 py1
+    __shared__ float4 s_b[256];          // inv v0 v1 v2
+    __shared__ float2 s_c[256];          // nf, code
+    __shared__ unsigned s_work[3];       // tile, first pair, pair count
+    const unsigned n_seg = a.counters->n_segments;
+    if (n_seg == 0u) return;
+    for (int i = threadIdx.x; i < LUT_TOTAL; i += blockDim.x) s_lut[i] = a.lut[i];
+    // each warp owns an 8 x 4 pixel block of the tile (2 x 4 blocks per tile): tighter warp-level culling than rows
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx = (warp & 1) * 8, by = (warp >> 1) * 4;
+    const int lx = bx + (lane & 7), ly = by + (lane >> 3);
+
+    for (;;) {
+        __syncthreads();                                  // s_work / batch buffers free (and LUT loaded on round 0)
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(&a.counters->work_counter, 1u);
+            if (ticket < n_seg) {
+                const unsigned l = a.seg_tile[ticket];
+                const unsigned first = a.tile_offset[l] + (ticket - a.seg_prefix[l]) * SEG;
+                const unsigned end = a.tile_offset[l + 1];
+                s_work[0] = l; s_work[1] = first; s_work[2] = min((unsigned)SEG, end - first);
+            } else {
+                s_work[0] = 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        const unsigned tile = s_work[0];
+        if (tile == 0xffffffffu) break;
+        const unsigned first = s_work[1], count = s_work[2];
+        const int tx = (int)(tile % (unsigned)a.ntx), ty = (int)(tile / (unsigned)a.ntx);
+        const int px = tx * TILE + lx, py = ty * TILE + ly;
+        const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+        // pixel-centre extent of this warp's block
+        const float wx0 = (float)(tx * TILE + bx) + 0.5f, wx1 = wx0 + 7.0f;
+        const float wy0 = (float)(ty * TILE + by) + 0.5f, wy1 = wy0 + 3.0f;
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+
+        for (unsigned b0 = 0; b0 < count; b0 += 256) {
+            const unsigned nb = min(256u, count - b0);
+            if (b0) __syncthreads();
+            if (threadIdx.x < nb) {
+                const unsigned ridx = a.pairs[first + b0 + threadIdx.x];
+                const float4 q0 = reinterpret_cast<const float4 *>(a.queue + ridx)[0];
+                const float4 q1 = reinterpret_cast<const float4 *>(a.queue + ridx)[1];
+                const float wpx = q1.x;
+                unsigned code; float nf;
+                if (wpx >= 64.0f) { code = 0x80000000u; nf = 64.0f; }
+                else {
+                    const int level = wpx > LEVEL_T0 ? 0 : wpx > LEVEL_T1 ? 1 : wpx > LEVEL_T2 ? 2 : 3;
+                    code = (unsigned)lut_offset(level); nf = (float)(64 >> level);
+                }
+                s_a[threadIdx.x] = q0;
+                s_b[threadIdx.x] = make_float4(1.0f / wpx, q1.y, q1.z, q1.w);
+                s_c[threadIdx.x] = make_float2(nf, __uint_as_float(code));
+            }
+            __syncthreads();
+            for (unsigned i = 0; i < nb; ++i) {
+                const float4 A = s_a[i];
+                // warp-uniform reject: the record's pixel-centre span misses this warp's 8x4 block
+                if (!(wx0 < A.y && wx1 >= A.x && wy0 < A.w && wy1 >= A.z)) continue;
+                if (fx >= A.x && fx < A.y && fy >= A.z && fy < A.w) {
+                    const float4 B = s_b[i];
+                    const float2 Cc = s_c[i];
+                    const float K = sample_lut_pre(s_lut, B.x, Cc.x, __float_as_uint(Cc.y), A.x, A.w, fx, fy);
+                    if (MODE == TSPLAT_MODE_RGB) {
+                        acc[0] += B.y * K; acc[1 % C] += B.z * K; acc[2 % C] += B.w * K; acc[3 % C] += 1.0f;
+                    } else {
+                        const float val = K * B.y;
+                        acc[0] += val;
+                        if (C == 2) acc[1 % C] += val * B.z;
+                    }
+                }
+            }
+        }
+        if (px < a.R && py < a.R) {
+            const size_t pix = (size_t)py * a.R + px;
+            if (C == 1) { if (acc[0] != 0.0f) atomicAdd(a.image + pix, acc[0]); }
+            else if (C == 2) {
+                if (acc[0] != 0.0f || acc[1 % C] != 0.0f)
+                    atomicAdd(reinterpret_cast<float2 *>(a.image) + pix, make_float2(acc[0], acc[1 % C]));
+            } else {
+                if (acc[3 % C] != 0.0f)
+                    atomicAdd(reinterpret_cast<float4 *>(a.image) + pix, make_float4(acc[0], acc[1 % C], acc[2 % C], acc[3 % C]));
             }
         }
     }
@@ -673,29 +1026,55 @@ extern "C" int tsplat_set_image(tsplat_ctx *c, float *image, int channels)
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct ScratchLayout {
-    int64_t queue_off, queue_cap;          // Deferred records
-    int64_t total;
+    int64_t queue_cap, pairs_cap;
+    int ntx, nt;
+    int64_t seg_cap;
+    int64_t queue_off, route_off, huge_off, tcount_off, toffset_off, tcursor_off, segpref_off, segtile_off, pairs_off, total;
 };
 
-static ScratchLayout scratch_layout(int R, int64_t bytes_or_particles, bool from_bytes)
+constexpr int64_t PAIRS_PER_PARTICLE = 6;     // pair capacity relative to the queue capacity (overflow -> atomic path)
+
+static ScratchLayout scratch_layout(int R, int64_t cap)
 {
-    (void)R;
     ScratchLayout L;
-    L.queue_off = 0;
-    if (from_bytes) {
-        L.queue_cap = bytes_or_particles / (int64_t)sizeof(Deferred);
-    } else {
-        L.queue_cap = bytes_or_particles;
-    }
-    if (L.queue_cap > 0xffffff00ll) L.queue_cap = 0xffffff00ll;
-    L.total = align_up(L.queue_cap * (int64_t)sizeof(Deferred), 256);
+    if (cap < 0) cap = 0;
+    if (cap > 0x7fffff00ll) cap = 0x7fffff00ll;
+    L.queue_cap = cap;
+    L.pairs_cap = cap * PAIRS_PER_PARTICLE;
+    if (L.pairs_cap > 0xfffffff0ll) L.pairs_cap = 0xfffffff0ll;
+    L.ntx = (R + TILE - 1) / TILE;
+    L.nt = L.ntx * L.ntx;
+    int64_t o = 0;
+    L.queue_off = o;   o += align_up(cap * (int64_t)sizeof(Deferred), 256);
+    L.route_off = o;   o += align_up(cap, 256);
+    L.huge_off = o;    o += align_up(cap * 4, 256);
+    L.tcount_off = o;  o += align_up(((int64_t)L.nt + 1) * 4, 256);
+    L.tcursor_off = o; o += align_up(((int64_t)L.nt + 1) * 4, 256);      // contiguous with tcount: one memset clears both
+    L.toffset_off = o; o += align_up(((int64_t)L.nt + 1) * 4, 256);
+    L.segpref_off = o; o += align_up(((int64_t)L.nt + 1) * 4, 256);
+    L.seg_cap = (int64_t)L.nt + L.pairs_cap / SEG + 1;
+    L.segtile_off = o; o += align_up(L.seg_cap * 4, 256);
+    L.pairs_off = o;   o += align_up(L.pairs_cap * 4, 256);
+    L.total = o;
     return L;
+}
+
+// largest queue capacity whose layout fits in `bytes`
+static ScratchLayout scratch_layout_from_bytes(int R, int64_t bytes)
+{
+    int64_t lo = 0, hi = bytes / (int64_t)sizeof(Deferred) + 1;      // layout(lo) fits (or nothing does), layout(hi) does not
+    if (scratch_layout(R, 0).total > bytes) return scratch_layout(R, 0);
+    while (hi - lo > 1) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (scratch_layout(R, mid).total <= bytes) lo = mid; else hi = mid;
+    }
+    return scratch_layout(R, lo);
 }
 
 extern "C" int64_t tsplat_scratch_bytes(int resolution, int64_t max_particles_per_call)
 {
     if (max_particles_per_call < 0) return -1;
-    return scratch_layout(resolution, max_particles_per_call, false).total;
+    return scratch_layout(resolution, max_particles_per_call).total;
 }
 
 extern "C" int tsplat_set_scratch(tsplat_ctx *c, void *scratch, int64_t bytes)
@@ -708,11 +1087,15 @@ extern "C" int tsplat_set_scratch(tsplat_ctx *c, void *scratch, int64_t bytes)
 }
 
 template <int MODE>
-static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups, cudaStream_t st)
+static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups, const ScratchLayout &L, cudaStream_t st)
 {
     const int threads = K1_THREADS;
     const int64_t blocks = (n_groups + threads - 1) / threads;
     if (blocks > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
+    char *sc = static_cast<char *>(c->scratch);
+    // per-call state: q_count .. pad, tile counters and cursors
+    CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, 6 * sizeof(unsigned int), st));
+    CUDA_TRY(cudaMemsetAsync(sc + L.tcount_off, 0, (size_t)(L.tcursor_off - L.tcount_off) * 2, st));
     if (blocks > 0) {
         // cell width of the vector REDs: as many pixels as fit 128 bits, if rows keep the cells aligned
         constexpr int CW = ModeTraits<MODE>::C == 1 ? 4 : ModeTraits<MODE>::C == 2 ? 2 : 1;
@@ -720,12 +1103,47 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
         else k_project_splat<MODE, 1><<<(unsigned)blocks, threads, 0, st>>>(pa);
         c->launches++;
     }
-    QueueArgs qa;
-    qa.queue = pa.queue; qa.indices = nullptr; qa.count = &c->d_counters->q_count; qa.cap = pa.queue_cap;
-    qa.lut = c->d_lut; qa.image = c->image; qa.R = c->R;
     if (pa.queue_cap > 0) {
+        BinArgs ba;
+        ba.queue = pa.queue; ba.queue_cap = pa.queue_cap; ba.counters = c->d_counters;
+        ba.route = reinterpret_cast<unsigned char *>(sc + L.route_off);
+        ba.huge_idx = reinterpret_cast<unsigned int *>(sc + L.huge_off);
+        ba.tile_count = reinterpret_cast<unsigned int *>(sc + L.tcount_off);
+        ba.tile_cursor = reinterpret_cast<unsigned int *>(sc + L.tcursor_off);
+        ba.tile_offset = reinterpret_cast<unsigned int *>(sc + L.toffset_off);
+        ba.seg_prefix = reinterpret_cast<unsigned int *>(sc + L.segpref_off);
+        ba.pairs = reinterpret_cast<unsigned int *>(sc + L.pairs_off);
+        ba.pairs_cap = (unsigned)L.pairs_cap;
+        ba.R = c->R; ba.ntx = L.ntx; ba.nt = L.nt;
+        ba.seg_tile = reinterpret_cast<unsigned int *>(sc + L.segtile_off);
+        ba.seg_cap = (unsigned)L.seg_cap;
+        const size_t hist_bytes = (size_t)L.nt * sizeof(unsigned);
+        const bool use_smem = 2 * hist_bytes <= 200 * 1024;
+        const int bin_grid = c->sm_count;
+        if (use_smem) {
+            if (!c->bin_attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(k_bin_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                CUDA_TRY(cudaFuncSetAttribute(k_bin_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                c->bin_attr_set = true;
+            }
+            k_bin_count<true><<<bin_grid, 1024, hist_bytes, st>>>(ba);
+            k_bin_scan<<<1, 1024, 0, st>>>(ba);
+            k_bin_fill<true><<<bin_grid, 1024, 2 * hist_bytes, st>>>(ba);
+        } else {
+            k_bin_count<false><<<bin_grid, 1024, 0, st>>>(ba);
+            k_bin_scan<<<1, 1024, 0, st>>>(ba);
+            k_bin_fill<false><<<bin_grid, 1024, 0, st>>>(ba);
+        }
+        GatherArgs ga;
+        ga.queue = pa.queue; ga.pairs = ba.pairs; ga.tile_offset = ba.tile_offset; ga.seg_prefix = ba.seg_prefix;
+        ga.seg_tile = ba.seg_tile;
+        ga.counters = c->d_counters; ga.lut = c->d_lut; ga.image = c->image; ga.R = c->R; ga.ntx = L.ntx; ga.nt = L.nt;
+        k_tile_gather<MODE><<<c->sm_count * 6, 256, 0, st>>>(ga);
+        QueueArgs qa;
+        qa.queue = pa.queue; qa.indices = ba.huge_idx; qa.count = &c->d_counters->huge_count; qa.cap = pa.queue_cap;
+        qa.lut = c->d_lut; qa.image = c->image; qa.R = c->R;
         k_queue_atomic<MODE><<<c->sm_count * 8, 256, 0, st>>>(qa);
-        c->launches++;
+        c->launches += 5;
     }
     CUDA_TRY(cudaGetLastError());
     return TSPLAT_OK;
@@ -756,7 +1174,7 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
         CUDA_TRY(cudaMemsetAsync(c->image, 0, sizeof(float) * (size_t)c->R * c->R * C, st));
         CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), st));
     }
-    const ScratchLayout L = scratch_layout(c->R, c->scratch_bytes, true);
+    const ScratchLayout L = scratch_layout_from_bytes(c->R, c->scratch_bytes);
 
     // validate + count
     int64_t one_start = 0, one_len = c->n;
@@ -786,15 +1204,14 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
     const int64_t chunk_cap = L.queue_cap;
     int rc = TSPLAT_OK;
     auto submit = [&](const ProjectArgs &args, int64_t n_groups, int64_t n_particles) -> int {
-        CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, 6 * sizeof(unsigned int), st));
         ProjectArgs a2 = args;
         a2.queue_cap = (unsigned)(chunk_cap < n_particles ? chunk_cap : n_particles);
         a2.n_groups = n_groups;
         switch (mode) {
-        case TSPLAT_MODE_DENSITY: return launch_render<TSPLAT_MODE_DENSITY>(c, a2, n_groups, st);
-        case TSPLAT_MODE_WEIGHTED: return launch_render<TSPLAT_MODE_WEIGHTED>(c, a2, n_groups, st);
-        case TSPLAT_MODE_RGB: return launch_render<TSPLAT_MODE_RGB>(c, a2, n_groups, st);
-        default: return launch_render<TSPLAT_MODE_DEPTH>(c, a2, n_groups, st);
+        case TSPLAT_MODE_DENSITY: return launch_render<TSPLAT_MODE_DENSITY>(c, a2, n_groups, L, st);
+        case TSPLAT_MODE_WEIGHTED: return launch_render<TSPLAT_MODE_WEIGHTED>(c, a2, n_groups, L, st);
+        case TSPLAT_MODE_RGB: return launch_render<TSPLAT_MODE_RGB>(c, a2, n_groups, L, st);
+        default: return launch_render<TSPLAT_MODE_DEPTH>(c, a2, n_groups, L, st);
         }
     };
 
