@@ -661,14 +661,21 @@ struct GatherArgs {
     int R, ntx, nt;
 };
 
-// same arithmetic as sample_lut(), with the per-record level decode hoisted: nf = texels per side (float),
-// code = lut offset | (bilinear << 31)
-__device__ __forceinline__ float sample_lut_pre(const float *__restrict__ lut, float inv, float nf, unsigned code,
-                                                float px0, float py1, float fx, float fy)
+// Per-record sampling constants hoisted out of the pixel loop.  Bit-identical to sample_lut():
+//   nearest:  floor(((fx - px0) * inv) * n) == floor((fx - px0) * (inv * n))   because n is a power of two,
+//             and the lower clamp is dropped because a covered pixel has fx >= px0 (and fy < py1), so u, v >= 0.
+struct GatherRec {
+    float4 a;       // px0 px1 py0 py1
+    float4 b;       // scale (= inv * n, or inv when bilinear), v0, v1, v2
+    int n;          // texels per side, 0 => bilinear on level 0
+    int base;       // float offset of the level inside the LUT
+};
+
+__device__ __forceinline__ float sample_rec(const float *__restrict__ lut, float scale, int n, int base,
+                                            float px0, float py1, float fx, float fy)
 {
-    const float u = (fx - px0) * inv;
-    const float v = (py1 - fy) * inv;
-    if (code & 0x80000000u) {
+    if (n == 0) {           // magnification: bilinear on the 64 x 64 level
+        const float u = (fx - px0) * scale, v = (py1 - fy) * scale;
         const float tu = fmaf(u, 64.0f, -0.5f), tv = fmaf(v, 64.0f, -0.5f);
         const float iu = floorf(tu), iv = floorf(tv);
         const float fu = tu - iu, fv = tv - iv;
@@ -681,25 +688,27 @@ __device__ __forceinline__ float sample_lut_pre(const float *__restrict__ lut, f
         const float bot = fmaf(fu, t11 - t10, t10);
         return fmaf(fv, bot - top, top);
     }
-    const int n = (int)nf;
-    const int iu = min(max(__float2int_rd(u * nf), 0), n - 1);
-    const int iv = min(max(__float2int_rd(v * nf), 0), n - 1);
-    return lut[(code & 0x7fffffffu) + iv * n + iu];
+    const int iu = min(__float2int_rd((fx - px0) * scale), n - 1);
+    const int iv = min(__float2int_rd((py1 - fy) * scale), n - 1);
+    return lut[base + iv * n + iu];
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
 {
     constexpr int C = ModeTraits<MODE>::C;
+    constexpr int BATCH = 256;
     __shared__ float s_lut[LUT_TOTAL];
-    __shared__ float4 s_a[256];          // px0 px1 py0 py1
-    __shared__ float4 s_b[256];          // inv v0 v1 v2
-    __shared__ float2 s_c[256];          // nf, code
-    __shared__ unsigned s_work[3];       // tile, first pair, pair count
+    __shared__ float4 s_a[BATCH];                 // px0 px1 py0 py1
+    __shared__ float4 s_b[BATCH];                 // scale v0 v1 v2
+    __shared__ int2 s_c[BATCH];                   // n, base
+    __shared__ unsigned char s_list[8][BATCH];    // per-warp list of the batch records that touch the warp's block
+    __shared__ unsigned s_nlist[8];
+    __shared__ unsigned s_work[3];                // tile, first pair, pair count
     const unsigned n_seg = a.counters->n_segments;
     if (n_seg == 0u) return;
     for (int i = threadIdx.x; i < LUT_TOTAL; i += blockDim.x) s_lut[i] = a.lut[i];
-    // each warp owns an 8 x 4 pixel block of the tile (2 x 4 blocks per tile): tighter warp-level culling than rows
+    // each warp owns an 8 x 4 pixel block of the tile (2 x 4 blocks per tile)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bx = (warp & 1) * 8, by = (warp >> 1) * 4;
     const int lx = bx + (lane & 7), ly = by + (lane >> 3);
@@ -717,6 +726,7 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                 s_work[0] = 0xffffffffu;
             }
         }
+        if (threadIdx.x < 8) s_nlist[threadIdx.x] = 0u;
         __syncthreads();
         const unsigned tile = s_work[0];
         if (tile == 0xffffffffu) break;
@@ -724,40 +734,49 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
         const int tx = (int)(tile % (unsigned)a.ntx), ty = (int)(tile / (unsigned)a.ntx);
         const int px = tx * TILE + lx, py = ty * TILE + ly;
         const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-        // pixel-centre extent of this warp's block
-        const float wx0 = (float)(tx * TILE + bx) + 0.5f, wx1 = wx0 + 7.0f;
-        const float wy0 = (float)(ty * TILE + by) + 0.5f, wy1 = wy0 + 3.0f;
+        const float tcx = (float)(tx * TILE) + 0.5f, tcy = (float)(ty * TILE) + 0.5f;   // first pixel centre of the tile
         float acc[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 0.0f;
 
-        for (unsigned b0 = 0; b0 < count; b0 += 256) {
-            const unsigned nb = min(256u, count - b0);
-            if (b0) __syncthreads();
+        for (unsigned b0 = 0; b0 < count; b0 += BATCH) {
+            const unsigned nb = min((unsigned)BATCH, count - b0);
+            if (b0) {
+                __syncthreads();
+                if (threadIdx.x < 8) s_nlist[threadIdx.x] = 0u;
+                __syncthreads();
+            }
             if (threadIdx.x < nb) {
                 const unsigned ridx = a.pairs[first + b0 + threadIdx.x];
                 const float4 q0 = reinterpret_cast<const float4 *>(a.queue + ridx)[0];
                 const float4 q1 = reinterpret_cast<const float4 *>(a.queue + ridx)[1];
-                const float wpx = q1.x;
-                unsigned code; float nf;
-                if (wpx >= 64.0f) { code = 0x80000000u; nf = 64.0f; }
+                const float wpx = q1.x, inv = 1.0f / wpx;
+                int n, base; float scale;
+                if (wpx >= 64.0f) { n = 0; base = 0; scale = inv; }
                 else {
                     const int level = wpx > LEVEL_T0 ? 0 : wpx > LEVEL_T1 ? 1 : wpx > LEVEL_T2 ? 2 : 3;
-                    code = (unsigned)lut_offset(level); nf = (float)(64 >> level);
+                    n = 64 >> level; base = lut_offset(level); scale = inv * (float)n;
                 }
                 s_a[threadIdx.x] = q0;
-                s_b[threadIdx.x] = make_float4(1.0f / wpx, q1.y, q1.z, q1.w);
-                s_c[threadIdx.x] = make_float2(nf, __uint_as_float(code));
+                s_b[threadIdx.x] = make_float4(scale, q1.y, q1.z, q1.w);
+                s_c[threadIdx.x] = make_int2(n, base);
+                // which of the 8 warp blocks (8 x 4 pixel centres each) does the record's span touch?
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const float x0 = tcx + (float)((w & 1) * 8), y0 = tcy + (float)((w >> 1) * 4);
+                    if (x0 < q0.y && x0 + 7.0f >= q0.x && y0 < q0.w && y0 + 3.0f >= q0.z)
+                        s_list[w][atomicAdd(&s_nlist[w], 1u)] = (unsigned char)threadIdx.x;
+                }
             }
             __syncthreads();
-            for (unsigned i = 0; i < nb; ++i) {
-                const float4 A = s_a[i];
-                // warp-uniform reject: the record's pixel-centre span misses this warp's 8x4 block
-                if (!(wx0 < A.y && wx1 >= A.x && wy0 < A.w && wy1 >= A.z)) continue;
+            const unsigned nl = s_nlist[warp];
+            for (unsigned i = 0; i < nl; ++i) {
+                const unsigned r = s_list[warp][i];
+                const float4 A = s_a[r];
                 if (fx >= A.x && fx < A.y && fy >= A.z && fy < A.w) {
-                    const float4 B = s_b[i];
-                    const float2 Cc = s_c[i];
-                    const float K = sample_lut_pre(s_lut, B.x, Cc.x, __float_as_uint(Cc.y), A.x, A.w, fx, fy);
+                    const float4 B = s_b[r];
+                    const int2 Cc = s_c[r];
+                    const float K = sample_rec(s_lut, B.x, Cc.x, Cc.y, A.x, A.w, fx, fy);
                     if (MODE == TSPLAT_MODE_RGB) {
                         acc[0] += B.y * K; acc[1 % C] += B.z * K; acc[2 % C] += B.w * K; acc[3 % C] += 1.0f;
                     } else {
