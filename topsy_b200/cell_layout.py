@@ -110,14 +110,15 @@ class CellLayout:
         lo, hi = pos.min().item(), pos.max().item()
         if lo < box_min or hi >= box_max:
             raise ValueError("Particle positions are outside the box")
-        # scalars exactly as numpy would form them for an array of this dtype (NEP 50: python floats are weak)
-        bmin = np_dtype(box_min) if not isinstance(box_min, np.generic) else box_min
-        bmax = np_dtype(box_max) if not isinstance(box_max, np.generic) else box_max
-        cell_size, centres = cls._grid(bmin, bmax, nside)
-        # the kernel evaluates (pos - box_min) / cell_size in the position dtype
-        sub_min = np.result_type(np_dtype, bmin)(bmin) if np.result_type(np_dtype, bmin) == np_dtype else None
-        if sub_min is None or np.result_type(np_dtype, cell_size) != np_dtype:
+        # scalars exactly as numpy would form them for an array of this dtype (NEP 50: python floats are weak,
+        # numpy scalars keep their own precision)
+        bmin = box_min if isinstance(box_min, np.generic) else np_dtype(box_min)
+        bmax = box_max if isinstance(box_max, np.generic) else np_dtype(box_max)
+        if np.result_type(np_dtype, bmin.dtype) != np_dtype or np.result_type(np_dtype, bmax.dtype) != np_dtype:
             raise ValueError("box scalars of higher precision than the positions are not supported on the device path")
+        cell_size, centres = cls._grid(bmin, bmax, nside)
+        sub_min = np_dtype(bmin)                      # the kernel evaluates (pos - box_min) / cell_size in the position dtype
+        cell_size = np_dtype(cell_size)
         n = pos.shape[0]
         lib = N.lib()
         dev = pos.device
@@ -127,7 +128,7 @@ class CellLayout:
         work = torch.empty(lib.tsplat_cell_layout_work_bytes(n, nside), dtype=torch.uint8, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         N.check(lib.tsplat_cell_layout(dev.index, ctypes.c_void_p(pos.data_ptr()), n, pos.element_size(),
-                                       ctypes.c_double(float(sub_min)), ctypes.c_double(float(np_dtype(cell_size))), nside,
+                                       ctypes.c_double(float(sub_min)), ctypes.c_double(float(cell_size)), nside,
                                        ctypes.c_void_p(order.data_ptr()), ctypes.c_void_p(lengths.data_ptr()),
                                        ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()),
                                        work.numel(), stream))
