@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=None, help="override particles per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl"], help="image sum method for N > 1")
     return ap.parse_args()
 
 
@@ -163,7 +164,7 @@ def run_reference(args):
     # bounded sample: calibrate on 2e5 particles, then size each step to ~3 s of CPU work
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     n_gen = min(wl.n_particles if args.particles is None else args.particles, 20_000_000)
-    data = synthetic.generate(wl, dev, n_total=n_total, n=n_gen)
+    data = synthetic.generate(wl, dev, n_total=wl.n_particles if args.particles is None else args.particles, n=n_gen)
     host = {k: v.cpu().numpy() for k, v in data.items()}
     del data
     rate0, _, cores = cpu_port_rate(wl, host, min(200_000, n_gen))
@@ -222,17 +223,19 @@ def run_ours(args):
     R = wl.resolution
     mode = MODE_ID[wl.mode]
     C = N.MODE_CHANNELS[mode]
-    data = synthetic.generate(wl, dev, n_total=n_total, rank=rank, n=n)
+    data = synthetic.generate(wl, dev, n_total=n, rank=rank, n=n)     # footprints fixed per GPU: weak scaling keeps per-GPU work constant
     names = synthetic.weight_names(wl.mode)
     M, sf = camera_for(wl)
 
-    eng = SplatEngine(R, device=local_rank)
+    from topsy_b200.distributed import ShardedSplat
+    sharded = ShardedSplat(R, C, reduce=args.reduce)
+    eng = sharded.engine
     eng.set_camera(M, sf)
     eng.set_particles(data["x"], data["y"], data["z"], data["h"])
     eng.set_weights(*[data[k] for k in names])
     blocks = export_blocks(n)
-    img = eng.image(C)
-    out = torch.empty((R, R, 4), dtype=torch.uint8, device=dev)
+    img = sharded.image
+    out = sharded.out
 
     # colormap stage: rgb -> tri-band log/gamma map; density/weighted -> log10 + 1-D LUT (implementation.py)
     params = N.ColormapParams()
@@ -245,20 +248,18 @@ def run_ours(args):
         lut = torch.from_numpy(luts.colormap_table_1d("twilight_shifted", 1000)).to(dev)
 
     def frame(ev=None):
-        for bi, (s, l) in enumerate(blocks):
-            eng.render(mode, [s], [l], clear=(bi == 0))
+        sharded.splat(mode, blocks)
         if ev is not None:
             ev[0].record()
-        if world > 1:
-            dist.all_reduce(img, op=dist.ReduceOp.SUM)
+        sharded.present(params, lut)
         if ev is not None:
             ev[1].record()
-        eng.colormap(img, params, lut, out, N.FMT_RGBA8)
 
     # one untimed frame to fix vmin/vmax from the image (autorange percentiles, implementation.py:381-425,512-531)
     frame()
     torch.cuda.synchronize()
-    ch = img[..., :3] if wl.mode == "rgb" else (img[..., 1] / img[..., 0] if wl.mode == "weighted" else img[..., 0])
+    full = sharded.reduced_image()
+    ch = full[..., :3] if wl.mode == "rgb" else (full[..., 1] / full[..., 0] if wl.mode == "weighted" else full[..., 0])
     v = torch.log10(ch[ch > 0].flatten().float())
     if v.numel() > 200:
         sub = v[torch.randint(0, v.numel(), (min(v.numel(), 2_000_000),), device=dev)]
@@ -276,14 +277,15 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for e in evs:
+        e[2] = e[3]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         evs[k][0].record()
-        frame(ev=(evs[k][1], evs[k][2]))
-        evs[k][3].record()
+        frame(ev=(evs[k][1], evs[k][3]))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -293,8 +295,7 @@ def run_ours(args):
     launches = st["kernel_launches"] - launches0
     total_ms = evs[0][0].elapsed_time(evs[-1][3])
     splat_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    reduce_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    cmap_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    present_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     t = torch.tensor([total_ms, splat_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,8 +355,10 @@ def run_ours(args):
                        "generator": "uniform box, lognormal h (topsy_b200/synthetic.py)", "h_factor": wl.h_factor,
                        "footprint_px": footprint_stats(h_cpu, wl), "blocks_per_frame": len(blocks),
                        "l2_policy": "inputs (%.2f GB per frame) exceed the 126 MB L2; no flush needed" % (bytes_alg / 1e9),
-                       "parallelism": f"particle shards x{world}, image all-reduce" if world > 1 else "single GPU"},
-            "phases_ms": {"splat": splat_ms_max, "reduce": reduce_ms, "colormap": cmap_ms},
+                       "parallelism": (f"particle shards x{world}; image sum = {sharded.method} "
+                                       f"({'fused reduce+colormap kernel over NVLink peer memory' if sharded.method == 'p2p' else 'NCCL reduce + colormap'})")
+                       if world > 1 else "single GPU"},
+            "phases_ms": {"splat": splat_ms_max, "reduce_and_colormap": present_ms},
             "roofline": {"bound": "hbm", "kernel": "k_project_splat (+ deferred queue kernels) per frame",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_frame": bytes_alg, "traffic": None,

@@ -125,6 +125,15 @@ int tsplat_colormap(tsplat_ctx *ctx, const float *image, int image_res, int chan
                     const tsplat_colormap_params *params, const float *lut, int lut_w, int lut_h,
                     void *out, int out_w, int out_h, int out_fmt, void *stream);
 
+/* Multi-GPU presentation (no reference counterpart: topsy is single-device).  Sums rows [row0, row0+nrows) of the
+ * n_peers partial accumulation images (device pointers, typically NVLink peer mappings of every rank's image, passed
+ * as a HOST array), in rank order; optionally stores the fp32 sum into sum_out (full-image base pointer, may be a peer
+ * mapping) and/or the colormapped RGBA into out (full-image base pointer of out_fmt, may be a peer mapping).
+ * Fuses reduce-scatter + colormap + gather into one kernel over peer memory. */
+int tsplat_reduce_colormap(tsplat_ctx *ctx, const float *const *peer_images, int n_peers, int channels,
+                           int row0, int nrows, const tsplat_colormap_params *params, const float *lut,
+                           int lut_w, int lut_h, void *out, int out_fmt, float *sum_out, void *stream);
+
 /* out[i] = a[i] + b[i] * scale, used by PeriodicSPH-style accumulation and by tests (device pointers). */
 int tsplat_image_axpy(tsplat_ctx *ctx, float *dst, const float *src, float scale, int64_t n, void *stream);
 

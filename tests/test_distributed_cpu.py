@@ -1,0 +1,100 @@
+"""Multi-GPU host logic on CPU: sharding arithmetic, and the image sum over a world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from topsy_b200 import distributed as D
+from topsy_b200.cell_layout import CellLayout
+from topsy_b200.drawreason import DrawReason
+from topsy_b200.progressive_render import RenderProgressionWithCells
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_striping_partitions_every_cell(world):
+    rs = np.random.RandomState(1)
+    lengths = rs.randint(0, 50, 64)
+    lengths[:3] = [0, 1, 7]
+    offsets = np.cumsum(lengths) - lengths
+    seen = np.zeros(lengths.sum(), dtype=int)
+    for r in range(world):
+        idx = D.shard_indices(offsets, lengths, r, world)
+        mine = D.shard_cell_lengths(lengths, r, world)
+        assert len(idx) == mine.sum()
+        assert (np.diff(idx) > 0).all() if len(idx) > 1 else True     # monotonic: cells stay contiguous and ordered
+        seen[idx] += 1
+        assert (mine <= -(-lengths // world)).all() and (mine >= lengths // world).all()     # balanced inside each cell
+    assert (seen == 1).all()
+    assert sum(D.shard_cell_lengths(lengths, r, world) for r in range(world)).tolist() == lengths.tolist()
+
+
+def test_shards_keep_cell_structure_for_the_progression():
+    """Each rank can run the unchanged progression on its own per-cell lengths: blocks never straddle cells and together
+    cover the shard exactly once."""
+    rs = np.random.RandomState(4)
+    pos = rs.uniform(0, 1, (20000, 3))
+    layout, order = CellLayout.from_positions(pos, 0.0, 1.0, 8)
+    for rank in range(2):
+        lens = D.shard_cell_lengths(layout._lengths, rank, 2)
+        offs = np.cumsum(lens) - lens
+        local = CellLayout(layout._centres, offs, lens)
+        rp = RenderProgressionWithCells(local, int(lens.sum()), 500)
+        hits = np.zeros(int(lens.sum()), dtype=int)
+        rp.start_frame(DrawReason.CHANGE)
+        while True:
+            for s, l in zip(*rp.get_block(0.0)):
+                hits[s:s + l] += 1
+            rp.end_block(1.0)
+            rp.end_frame_get_scalefactor()
+            if not rp.needs_refine():
+                break
+            rp.start_frame(DrawReason.REFINE)
+        assert (hits == 1).all()
+
+
+def test_row_slabs_tile_the_image():
+    for R in (200, 2048, 4097):
+        for world in (1, 2, 3, 8):
+            rows = [D.row_slab(R, r, world) for r in range(world)]
+            assert rows[0][0] == 0 and sum(n for _, n in rows) == R
+            for (a, n), (b, _) in zip(rows, rows[1:]):
+                assert a + n == b
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(100 + rank)
+        part = torch.from_numpy(rs.uniform(size=(32, 32, 2)).astype(np.float32))
+        total = D.reduce_image_host(part.clone())
+        q.put((rank, total.numpy(), part.numpy()))
+        only0 = D.reduce_image_host(part.clone(), dst=0)
+        if rank == 0:
+            assert torch.equal(only0, total)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_image_sum_over_gloo_world_of_two():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got.sort(key=lambda t: t[0])
+    want = got[0][2] + got[1][2]
+    np.testing.assert_allclose(got[0][1], want, rtol=1e-6)
+    np.testing.assert_allclose(got[1][1], want, rtol=1e-6)

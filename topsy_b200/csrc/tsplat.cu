@@ -858,6 +858,51 @@ __device__ __forceinline__ void load_pixel(const float *__restrict__ img, int re
     else { const float4 t = reinterpret_cast<const float4 *>(img)[pix]; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 }
 
+// value -> colour: the body of fragment_main / fragment_main_tri (colormap.wgsl:79-159)
+__device__ __forceinline__ float4 colormap_value(const float v[4], const tsplat_colormap_params &p,
+                                                 const float *__restrict__ lut, int lut_w, int lut_h)
+{
+    if (p.kind == TSPLAT_CMAP_RGB) {
+        float c3[3] = {v[0], v[1], v[2]};
+        for (int c = 0; c < 3; ++c) {
+            float val = c3[c];
+            if (p.log_scale) val = wgsl_log10(val);
+            const float t = fmaxf((val - p.vmin) / (p.vmax - p.vmin), 0.0f);
+            c3[c] = powf(t, p.gamma);
+        }
+        return make_float4(c3[0], c3[1], c3[2], 1.0f);
+    }
+    const bool weighted = (p.kind == TSPLAT_CMAP_WEIGHTED || p.kind == TSPLAT_CMAP_BIVARIATE_WEIGHTED);
+    float val = weighted ? v[1] / v[0] : v[0];
+    if (p.log_scale) val = wgsl_log10(val);
+    const float t = clamp01((val - p.vmin) / (p.vmax - p.vmin));
+    if (p.kind == TSPLAT_CMAP_BIVARIATE || p.kind == TSPLAT_CMAP_BIVARIATE_WEIGHTED) {
+        const float d = clamp01((wgsl_log10(v[0]) - p.density_vmin) / (p.density_vmax - p.density_vmin));
+        return lut_sample_2d(lut, lut_w, lut_h, d, t);
+    }
+    return lut_sample_1d(lut, lut_w, t);
+}
+
+__device__ __forceinline__ void store_rgba(void *out, size_t o, int out_fmt, float4 rgba)
+{
+    if (out_fmt == TSPLAT_FMT_RGBA8) {
+        uchar4 q;
+        q.x = (unsigned char)__float2int_rn(__saturatef(rgba.x) * 255.0f);
+        q.y = (unsigned char)__float2int_rn(__saturatef(rgba.y) * 255.0f);
+        q.z = (unsigned char)__float2int_rn(__saturatef(rgba.z) * 255.0f);
+        q.w = (unsigned char)__float2int_rn(__saturatef(rgba.w) * 255.0f);
+        reinterpret_cast<uchar4 *>(out)[o] = q;
+    } else if (out_fmt == TSPLAT_FMT_RGBA16F) {
+        __half2 lo = __floats2half2_rn(rgba.x, rgba.y), hi = __floats2half2_rn(rgba.z, rgba.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned int *>(&lo);
+        pk.y = *reinterpret_cast<unsigned int *>(&hi);
+        reinterpret_cast<uint2 *>(out)[o] = pk;
+    } else {
+        reinterpret_cast<float4 *>(out)[o] = rgba;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_colormap(const CmapArgs a)
 {
     const int ox = blockIdx.x * blockDim.x + threadIdx.x;
@@ -896,47 +941,50 @@ __global__ void __launch_bounds__(256) k_colormap(const CmapArgs a)
         }
     }
 
-    float4 rgba;
-    const tsplat_colormap_params &p = a.p;
-    if (p.kind == TSPLAT_CMAP_RGB) {
-        float c3[3] = {v[0], v[1], v[2]};
-        for (int c = 0; c < 3; ++c) {
-            float val = c3[c];
-            if (p.log_scale) val = wgsl_log10(val);
-            const float t = fmaxf((val - p.vmin) / (p.vmax - p.vmin), 0.0f);
-            c3[c] = powf(t, p.gamma);
-        }
-        rgba = make_float4(c3[0], c3[1], c3[2], 1.0f);
-    } else {
-        const bool weighted = (p.kind == TSPLAT_CMAP_WEIGHTED || p.kind == TSPLAT_CMAP_BIVARIATE_WEIGHTED);
-        float val = weighted ? v[1] / v[0] : v[0];
-        if (p.log_scale) val = wgsl_log10(val);
-        const float t = clamp01((val - p.vmin) / (p.vmax - p.vmin));
-        if (p.kind == TSPLAT_CMAP_BIVARIATE || p.kind == TSPLAT_CMAP_BIVARIATE_WEIGHTED) {
-            const float d = clamp01((wgsl_log10(v[0]) - p.density_vmin) / (p.density_vmax - p.density_vmin));
-            rgba = lut_sample_2d(a.lut, a.lut_w, a.lut_h, d, t);
-        } else {
-            rgba = lut_sample_1d(a.lut, a.lut_w, t);
-        }
-    }
+    const float4 rgba = colormap_value(v, a.p, a.lut, a.lut_w, a.lut_h);
+    store_rgba(a.out, (size_t)oy * a.out_w + ox, a.out_fmt, rgba);
+}
 
-    const size_t o = (size_t)oy * a.out_w + ox;
-    if (a.out_fmt == TSPLAT_FMT_RGBA8) {
-        uchar4 q;
-        q.x = (unsigned char)__float2int_rn(__saturatef(rgba.x) * 255.0f);
-        q.y = (unsigned char)__float2int_rn(__saturatef(rgba.y) * 255.0f);
-        q.z = (unsigned char)__float2int_rn(__saturatef(rgba.z) * 255.0f);
-        q.w = (unsigned char)__float2int_rn(__saturatef(rgba.w) * 255.0f);
-        reinterpret_cast<uchar4 *>(a.out)[o] = q;
-    } else if (a.out_fmt == TSPLAT_FMT_RGBA16F) {
-        __half2 lo = __floats2half2_rn(rgba.x, rgba.y), hi = __floats2half2_rn(rgba.z, rgba.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<unsigned int *>(&lo);
-        pk.y = *reinterpret_cast<unsigned int *>(&hi);
-        reinterpret_cast<uint2 *>(a.out)[o] = pk;
-    } else {
-        reinterpret_cast<float4 *>(a.out)[o] = rgba;
+// ------------------------------------------------------------------------------------------------------------
+// K6: fused image sum-reduce over NVLink peers + colormap (multi-GPU).  Every rank owns a slab of rows; it loads that
+// slab from every peer's accumulation image (peer pointers from PyTorch symmetric memory), adds the partial images in
+// rank order (deterministic), optionally stores the fp32 sum, applies the colormap and stores RGBA -- possibly into
+// another rank's buffer.  One kernel replaces reduce-scatter + colormap + gather.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 16;
+
+struct ReduceArgs {
+    const float *peer[MAX_PEERS];
+    int n_peers;
+    int res, channels;
+    int row0, nrows;
+    tsplat_colormap_params p;
+    const float *lut;
+    int lut_w, lut_h;
+    void *out;              // full R x R x 4 output image (row-major) or nullptr
+    int out_fmt;
+    float *sum_out;         // full R x R x C fp32 image receiving the reduced slab, or nullptr
+};
+
+__global__ void __launch_bounds__(256) k_reduce_colormap(const ReduceArgs a)
+{
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = a.row0 + blockIdx.y;
+    if (ox >= a.res || blockIdx.y >= (unsigned)a.nrows) return;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < a.n_peers; ++r) {
+        float t[4];
+        load_pixel(a.peer[r], a.res, a.channels, ox, oy, t);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] += t[c];
     }
+    const size_t pix = (size_t)oy * a.res + ox;
+    if (a.sum_out) {
+        if (a.channels == 1) a.sum_out[pix] = v[0];
+        else if (a.channels == 2) reinterpret_cast<float2 *>(a.sum_out)[pix] = make_float2(v[0], v[1]);
+        else reinterpret_cast<float4 *>(a.sum_out)[pix] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (a.out) store_rgba(a.out, pix, a.out_fmt, colormap_value(v, a.p, a.lut, a.lut_w, a.lut_h));
 }
 
 __global__ void k_axpy(float *__restrict__ dst, const float *__restrict__ src, float scale, int64_t n)
@@ -1310,6 +1358,38 @@ extern "C" int tsplat_colormap(tsplat_ctx *c, const float *image, int image_res,
     a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_w = out_w; a.out_h = out_h; a.out_fmt = out_fmt;
     dim3 grid((out_w + 255) / 256, out_h);
     k_colormap<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    c->launches++;
+    c->last_stream = (cudaStream_t)stream;
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_reduce_colormap(tsplat_ctx *c, const float *const *peer_images, int n_peers, int channels,
+                                      int row0, int nrows, const tsplat_colormap_params *params, const float *lut,
+                                      int lut_w, int lut_h, void *out, int out_fmt, float *sum_out, void *stream)
+{
+    if (!c || !peer_images) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (n_peers < 1 || n_peers > MAX_PEERS) return set_err(TSPLAT_ERR_INVALID, "n_peers must be in [1, %d]", MAX_PEERS);
+    if (channels != 1 && channels != 2 && channels != 4) return set_err(TSPLAT_ERR_INVALID, "channels must be 1, 2 or 4");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > c->R) return set_err(TSPLAT_ERR_INVALID, "row slab outside the image");
+    if (out && !params) return set_err(TSPLAT_ERR_INVALID, "colormap parameters missing");
+    if (out && (out_fmt < TSPLAT_FMT_RGBA8 || out_fmt > TSPLAT_FMT_RGBA32F)) return set_err(TSPLAT_ERR_INVALID, "bad output format");
+    if (out && params->kind != TSPLAT_CMAP_RGB && (!lut || lut_w <= 0 || lut_h <= 0))
+        return set_err(TSPLAT_ERR_INVALID, "colormap LUT missing");
+    if (out && params->kind == TSPLAT_CMAP_RGB && channels < 4) return set_err(TSPLAT_ERR_INVALID, "RGB map needs a 4-channel image");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (nrows == 0) return TSPLAT_OK;
+    ReduceArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_images[r]) return set_err(TSPLAT_ERR_INVALID, "NULL peer image %d", r);
+        a.peer[r] = peer_images[r];
+    }
+    a.n_peers = n_peers; a.res = c->R; a.channels = channels; a.row0 = row0; a.nrows = nrows;
+    if (params) a.p = *params;
+    a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_fmt = out_fmt; a.sum_out = sum_out;
+    dim3 grid((c->R + 255) / 256, nrows);
+    k_reduce_colormap<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,159 @@
+"""Multi-GPU SPH projection: particles shard, images sum (no reference counterpart -- topsy is single-device).
+
+One process per GPU (torchrun).  Splatting is a sum over particles, so each rank splats its shard into a full-resolution
+partial image and the only exchange is one image sum before the colormap:
+
+  * sharding    per-cell striping -- rank g takes every G-th particle of every cell (``shard_indices``).  Because the
+                within-cell order is a uniform shuffle, every rank holds a statistically identical subsample, so load is
+                balanced for any zoom, and cell selection / progressive fractions apply unchanged with the rank's own
+                per-cell lengths (``shard_cell_lengths``).
+  * reduce      'p2p'   (default on NVLink boxes): the partial images live in PyTorch symmetric memory; after a
+                        device-side barrier every rank runs ONE kernel (tsplat_reduce_colormap) that loads its slab of
+                        rows from every peer over NVLink, adds them in rank order, applies the colormap and stores the
+                        RGBA rows straight into rank 0's output -- reduce-scatter + colormap + gather fused.
+                'nccl'  baseline / fallback: ``dist.all_reduce`` (or ``reduce`` to rank 0) of the fp32 image, then the
+                        ordinary colormap kernel on rank 0.
+                'gloo'  CPU tensors, used by the world_size-2 CPU tests of the host logic only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# sharding arithmetic (pure numpy: tested on CPU)
+# ----------------------------------------------------------------------------------------------------------------
+def shard_cell_lengths(lengths: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Particles of each cell that land on ``rank`` under per-cell striping: ceil((len_c - rank) / world)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    return np.maximum(0, (lengths - rank + world - 1) // world)
+
+
+def shard_indices(offsets: np.ndarray, lengths: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Global indices (into the cell-sorted, shuffled order) owned by ``rank``: offset_c + rank + k*world."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    mine = shard_cell_lengths(lengths, rank, world)
+    total = int(mine.sum())
+    if total == 0:
+        return np.zeros(0, dtype=np.int64)
+    cell_of = np.repeat(np.arange(len(mine)), mine)
+    first = np.cumsum(mine) - mine
+    k = np.arange(total, dtype=np.int64) - first[cell_of]
+    return offsets[cell_of] + rank + k * world
+
+
+def row_slab(resolution: int, rank: int, world: int):
+    """Rows [row0, row0 + nrows) of the image that ``rank`` reduces and colormaps."""
+    base, extra = divmod(resolution, world)
+    row0 = rank * base + min(rank, extra)
+    return row0, base + (1 if rank < extra else 0)
+
+
+def reduce_image_host(image, group=None, dst: int | None = None):
+    """Sum a partial image over the process group with the backend's collective (NCCL on CUDA tensors, gloo on CPU)."""
+    import torch.distributed as dist
+    if dst is None:
+        dist.all_reduce(image, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(image, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return image
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device side
+# ----------------------------------------------------------------------------------------------------------------
+class ShardedSplat:
+    """One rank of a sharded render: local engine + the image exchange."""
+
+    def __init__(self, resolution: int, channels: int, out_format: str = "rgba8unorm", reduce: str = "auto", group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as N
+        from .engine import SplatEngine
+
+        self.N = N
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.group = group
+        self.resolution = resolution
+        self.channels = channels
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.engine = SplatEngine(resolution, device=self.device.index)
+        self.out_format = out_format
+        fmt, tdtype = {"rgba8unorm": (N.FMT_RGBA8, torch.uint8), "rgba16float": (N.FMT_RGBA16F, torch.float16),
+                       "rgba32float": (N.FMT_RGBA32F, torch.float32)}[out_format]
+        self._fmt = fmt
+        self.method = reduce
+        if reduce == "auto":
+            self.method = "p2p" if self.world > 1 else "local"
+        self._hdl = self._out_hdl = None
+        shape = (resolution, resolution, channels)
+        if self.method == "p2p" and self.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                self.image = symm.empty(shape, dtype=torch.float32, device=self.device)
+                self.out = symm.empty((resolution, resolution, 4), dtype=tdtype, device=self.device)
+                gname = (group or dist.group.WORLD).group_name
+                self._hdl = symm.rendezvous(self.image, gname)
+                self._out_hdl = symm.rendezvous(self.out, gname)
+                self.image.zero_()
+                self._peer_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self._hdl.buffer_ptrs])
+                self._out0 = int(self._out_hdl.buffer_ptrs[0])
+            except Exception as e:      # no peer access (e.g. PCIe-only box): fall back to the collective
+                if reduce == "p2p":
+                    raise
+                self.method = "nccl"
+                self._fallback_reason = repr(e)
+        if self.method != "p2p" or self.world == 1:
+            self.image = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            self.out = torch.empty((resolution, resolution, 4), dtype=tdtype, device=self.device)
+        self.engine.bind_image(self.image)
+
+    # -- frame ------------------------------------------------------------------------------------------------
+    def splat(self, mode, blocks):
+        """Local splat of this rank's particles (already set on ``self.engine``): list of (start, length) blocks."""
+        for i, (s, l) in enumerate(blocks):
+            self.engine.render(mode, [s], [l], clear=(i == 0), image=self.image)
+
+    def present(self, params, lut):
+        """Image sum over ranks + colormap.  The RGBA result is valid on rank 0 (``self.out``)."""
+        import torch.distributed as dist
+        N = self.N
+        eng = self.engine
+        if self.world == 1 or self.method == "local":
+            eng.colormap(self.image, params, lut, self.out, self._fmt)
+            return self.out
+        if self.method == "p2p":
+            import torch
+            self._hdl.barrier()                                   # every rank's partial image is complete and visible
+            row0, nrows = row_slab(self.resolution, self.rank, self.world)
+            lw, lh = (0, 0) if lut is None else ((lut.shape[0], 1) if lut.dim() == 2 else (lut.shape[1], lut.shape[0]))
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            N.check(eng.lib.tsplat_reduce_colormap(eng._ctx, self._peer_ptrs, self.world, self.channels, row0, nrows,
+                                                   ctypes.byref(params), None if lut is None else ctypes.c_void_p(lut.data_ptr()),
+                                                   lw, lh, ctypes.c_void_p(self._out0), self._fmt, None, stream))
+            self._out_hdl.barrier()                               # rank 0's output is complete; images may be cleared
+            return self.out
+        # nccl baseline: reduce a copy so that the partial image stays valid (progressive REFINE frames keep adding to it)
+        if getattr(self, "_sum", None) is None:
+            self._sum = self.image.clone()
+        else:
+            self._sum.copy_(self.image)
+        dist.reduce(self._sum, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+        if self.rank == 0:
+            eng.colormap(self._sum, params, lut, self.out, self._fmt)
+        return self.out
+
+    def reduced_image(self):
+        """fp32 sum image on every rank (for get_image-style readback and tests); collective."""
+        import torch.distributed as dist
+        img = self.image.clone()
+        if self.world > 1:
+            dist.all_reduce(img, op=dist.ReduceOp.SUM, group=self.group)
+        return img
+
+    def close(self):
+        self.engine.close()
