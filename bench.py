@@ -363,6 +363,11 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_frame": bytes_alg, "traffic": None,
                          "bytes_per_particle": wl.bytes_per_particle},
+            "atomic_roofline": {"bound": "vector RED issue rate (SM-side L1TEX limit; profiles/r01/atomics_bench_b200.txt)",
+                                "direct_vector_reds_per_frame": int(st["direct_vector_reds"]),
+                                "achieved": st["direct_vector_reds"] / (splat_ms_max * 1e-3), "peak": 1.9e11, "unit": "RED lanes/s",
+                                "frac": st["direct_vector_reds"] / (splat_ms_max * 1e-3) / 1.9e11,
+                                "reds_per_particle": st["direct_vector_reds"] / max(n, 1)},
             "gpu_launches": int(launches),
             "stats": {k: int(v) for k, v in st.items()},
             "wall_ms_per_step": t_wall * 1e3 / args.steps,

@@ -78,6 +78,7 @@ typedef struct {
     int64_t particles_huge;         /* deferred to the cooperative atomic path (footprint or pair overflow)    */
     int64_t tile_pairs;             /* (particle, tile) pairs processed by the gather path                     */
     int64_t kernel_launches;        /* CUDA kernels launched by this context since creation                    */
+    int64_t direct_vector_reds;     /* 128-bit (or narrower) REDs issued by the direct path since the last clear */
 } tsplat_stats;
 
 const char *tsplat_last_error(void);

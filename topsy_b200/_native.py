@@ -27,7 +27,8 @@ class ColormapParams(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in ("particles_submitted", "particles_culled", "particles_direct",
-                                              "particles_tiled", "particles_huge", "tile_pairs", "kernel_launches")]
+                                              "particles_tiled", "particles_huge", "tile_pairs", "kernel_launches",
+                                              "direct_vector_reds")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

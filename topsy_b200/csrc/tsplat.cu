@@ -55,7 +55,7 @@ constexpr float DIRECT_MAX_WPX = 8.0f;      // footprints up to this width are s
 constexpr float HUGE_MIN_WPX = 256.0f;      // footprints above this go to the cooperative atomic kernel
 
 struct Counters {
-    unsigned long long submitted, culled, direct, tiled, huge, pairs;
+    unsigned long long reds, culled, direct, tiled, huge, pairs;
     unsigned int q_count;        // deferred records in the queue (this call)
     unsigned int huge_count;     // records routed to the cooperative atomic kernel (this call)
     unsigned int pair_total;     // (particle, tile) pairs reserved (this call)
@@ -198,9 +198,9 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     __shared__ float s_lut8[64];
     __shared__ DirectRec s_rec[K1_WARPS][K1_RECS];
     __shared__ unsigned s_bits[K1_WARPS][K1_BITWORDS];
-    __shared__ unsigned s_cnt[3];                // culled, direct, deferred (this CTA)
+    __shared__ unsigned s_cnt[4];                // culled, direct, deferred, vector REDs issued (this CTA)
     if (threadIdx.x < 64) s_lut8[threadIdx.x] = a.lut[lut_offset(3) + threadIdx.x];
-    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         if (has_rec[e]) atomicOr(&s_bits[warp][head_off[e] >> 5], 1u << (head_off[e] & 31u));
     __syncwarp();
 
-    unsigned rec_base = 0;
+    unsigned rec_base = 0, n_reds = 0;
     for (unsigned wi = 0; wi < n_words; ++wi) {
         const unsigned word = s_bits[warp][wi];
         const unsigned t = (wi << 5) + lane;
@@ -349,8 +349,10 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
             const float fy = (float)k + 0.5f;
             if (CELL_W == 1) {
                 const float K = sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)cj + 0.5f, fy);
-                if (MODE == TSPLAT_MODE_RGB || K != 0.0f)            // adding +0 is a no-op; RGB still counts fragments
+                if (MODE == TSPLAT_MODE_RGB || K != 0.0f) {          // adding +0 is a no-op; RGB still counts fragments
                     red_pixel<MODE>(a.image, (size_t)k * a.R + cj, K, ra.w, rb.x, rb.y);
+                    ++n_reds;
+                }
             } else {
                 float Ks[CELL_W];
                 bool any = false;
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                     any |= (Ks[c] != 0.0f);
                 }
                 if (any) {
+                    ++n_reds;
                     const size_t pix = (size_t)k * a.R + (size_t)cj * CELL_W;
                     if (MODE == TSPLAT_MODE_DENSITY) {
                         atomicAdd(reinterpret_cast<float4 *>(a.image + pix),
@@ -379,10 +382,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     if (n_culled) atomicAdd(&s_cnt[0], n_culled);
     if (n_direct) atomicAdd(&s_cnt[1], n_direct);
     if (n_deferred) atomicAdd(&s_cnt[2], n_deferred);
+    for (int d = 16; d > 0; d >>= 1) n_reds += __shfl_down_sync(0xffffffffu, n_reds, d);
+    if (lane == 0 && n_reds) atomicAdd(&s_cnt[3], n_reds);
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_cnt[0]) atomicAdd(&a.counters->culled, (unsigned long long)s_cnt[0]);
         if (s_cnt[1]) atomicAdd(&a.counters->direct, (unsigned long long)s_cnt[1]);
+        if (s_cnt[3]) atomicAdd(&a.counters->reds, (unsigned long long)s_cnt[3]);
     }
 }
 
@@ -1442,6 +1448,7 @@ extern "C" int tsplat_get_stats(tsplat_ctx *c, tsplat_stats *out)
     out->particles_huge = (int64_t)h.huge;
     out->tile_pairs = (int64_t)h.pairs;
     out->particles_submitted = (int64_t)(h.culled + h.direct + h.tiled + h.huge);
+    out->direct_vector_reds = (int64_t)h.reds;
     out->kernel_launches = c->launches;
     return TSPLAT_OK;
 }
