@@ -100,9 +100,9 @@ static inline void bounds(float lo, float hi, int R, int *a, int *b)
     bounds(p.px0, p.px1, R, &j0, &j1);                                                                         \
     bounds(p.py0, p.py1, R, &k0, &k1);                                                                         \
     if (j1 < j0 || k1 < k0) continue;                                                                          \
-    float hh = h[i] * h[i];                                                                                    \
-    float i0 = w0[i] / hh, i1 = 0.0f, i2 = 0.0f;                                                               \
-    if (mode == MODE_RGB) { i1 = w1[i] / hh; i2 = w2[i] / hh; }                                                \
+    float rhh = 1.0f / (h[i] * h[i]);          /* one IEEE reciprocal, then multiplies (arithmetic contract) */ \
+    float i0 = w0[i] * rhh, i1 = 0.0f, i2 = 0.0f;                                                              \
+    if (mode == MODE_RGB) { i1 = w1[i] * rhh; i2 = w2[i] * rhh; }                                              \
     for (int k = k0; k <= k1; ++k) {                                                                           \
         float fy = (float)k + 0.5f;                                                                            \
         if (!(fy >= p.py0 && fy < p.py1)) continue;                                                            \

@@ -54,8 +54,12 @@ constexpr int RANGE_SLOTS = 4;              // pinned staging ring for range tab
 constexpr float DIRECT_MAX_WPX = 8.0f;      // footprints up to this width are splatted by the projecting thread
 constexpr float HUGE_MIN_WPX = 256.0f;      // footprints above this go to the cooperative atomic kernel
 
+constexpr int STAT_SLOTS = 256;             // power of two
+struct StatSlot { unsigned long long culled_direct, reds; };   // culled in the low 32 bits, direct in the high 32
+
 struct Counters {
     unsigned long long reds, culled, direct, tiled, huge, pairs;
+    StatSlot slots[STAT_SLOTS];  // K1's per-warp statistics land here (spread to avoid same-address atomics)
     unsigned int q_count;        // deferred records in the queue (this call)
     unsigned int huge_count;     // records routed to the cooperative atomic kernel (this call)
     unsigned int pair_total;     // (particle, tile) pairs reserved (this call)
@@ -169,16 +173,20 @@ __device__ __forceinline__ float4 ld4_tail(const float *__restrict__ p, int64_t 
 }
 
 // K1 works in two phases per warp so that the accumulation phase is divergence-free:
-//   phase A  every lane projects its 4 particles; small-footprint ones become 48-byte records in the warp's slice of
-//            shared memory, with the exclusive prefix of their "cell" counts; a bit vector marks segment heads.
-//   phase B  the warp walks the flattened (particle, cell) list 32 entries at a time; a cell is the group of CELL_W
-//            horizontally adjacent pixels that one 128-bit vector RED covers:
-//               RGB      4 channels -> 1 pixel     WEIGHTED/DEPTH 2 channels -> 2 pixels     DENSITY 1 channel -> 4 pixels
+//   phase A  every lane projects its 4 particles; small-footprint ones become 48-byte records in fixed slots of the
+//            warp's shared-memory slice.  ONE packed warp scan (cell counts | record counts) then gives every record its
+//            offset in the warp's flattened cell list and its rank among the non-empty records.
+//   phase B  the warp walks the flattened (particle, cell) list 32 entries at a time; a bit vector of segment heads +
+//            popc finds the owner record.  A cell is the group of CELL_W horizontally adjacent pixels that one 128-bit
+//            vector RED covers:  RGB 4 channels -> 1 pixel | WEIGHTED/DEPTH 2 channels -> 2 pixels | DENSITY -> 4 pixels
 constexpr int K1_THREADS = 128;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_RECS = 128;                 // records per warp batch (4 per lane)
 constexpr int K1_MAX_SPAN = 8;               // direct particles cover at most 8 x 8 pixel centres
 constexpr int K1_BITWORDS = K1_RECS * K1_MAX_SPAN * K1_MAX_SPAN / 32;
+
+// (t * c_magic[n]) >> 16 == t / n for t < 4096, n in 1..8      (ceil(65536 / n))
+__constant__ unsigned c_magic[9] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u};
 
 struct __align__(16) DirectRec {
     float px0, py1, inv, v0;
@@ -187,7 +195,7 @@ struct __align__(16) DirectRec {
     unsigned jj;         // first covered pixel column j0 (low 16) | last j1 (high 16)
     unsigned off;        // offset of the particle's first cell in the warp's flattened list
     unsigned ncj;        // cell columns
-    unsigned magic;      // ceil(65536 / ncj): (t * magic) >> 16 == t / ncj for t < 4096
+    unsigned magic;      // c_magic[ncj]
     unsigned pad;
 };
 
@@ -195,20 +203,22 @@ template <int MODE, int CELL_W>
 __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs a)
 {
     constexpr int CELL_SHIFT = CELL_W == 4 ? 2 : CELL_W == 2 ? 1 : 0;
-    __shared__ float s_lut8[64];
+    // Warps are fully independent (no block-wide barrier): every warp stages its own copy of the 8x8 LUT level, and the
+    // loads that feed it are issued together with the particle loads so that one memory latency covers both.
+    __shared__ float s_lut8w[K1_WARPS][64];
     __shared__ DirectRec s_rec[K1_WARPS][K1_RECS];
     __shared__ unsigned s_bits[K1_WARPS][K1_BITWORDS];
-    __shared__ unsigned s_cnt[4];                // culled, direct, deferred, vector REDs issued (this CTA)
-    if (threadIdx.x < 64) s_lut8[threadIdx.x] = a.lut[lut_offset(3) + threadIdx.x];
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
-    __syncthreads();
-
+    __shared__ unsigned char s_slot[K1_WARPS][K1_RECS];      // rank among non-empty records -> record slot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float2 lut_pair = __ldg(reinterpret_cast<const float2 *>(a.lut + lut_offset(3)) + lane);
+    const float *s_lut8 = s_lut8w[warp];
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t group = 0, lo = 0, hi = 0;
+    int64_t group = 0;
+    int e_first = 0, e_last = 0;                 // this lane's particles e in [e_first, e_last) are inside the range
     const bool active = gi < a.n_groups;
     if (active) {
+        int64_t lo, hi;
         if (a.table.n > 0) {
             int l = 0, r = a.table.n;            // invariant: gprefix[l] <= gi < gprefix[r]
             while (r - l > 1) {
@@ -221,6 +231,9 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         } else {
             lo = a.start; hi = a.end; group = a.g0 + gi;
         }
+        const int64_t base = group << 2;
+        e_first = (int)max((int64_t)0, lo - base);
+        e_last = (int)min((int64_t)4, hi - base);
     }
 
     // ---- phase A: load, project, classify ---------------------------------------------------------------
@@ -249,93 +262,86 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         w2s[0] = W2.x; w2s[1] = W2.y; w2s[2] = W2.z; w2s[3] = W2.w;
     }
 
+    reinterpret_cast<float2 *>(s_lut8w[warp])[lane] = lut_pair;
     unsigned n_culled = 0, n_direct = 0, n_deferred = 0;
-    unsigned run_cells = 0, run_recs = 0;         // warp-uniform running totals
-    unsigned head_off[4];
-    bool has_rec[4];
+    unsigned cells4 = 0;                          // cell counts of the lane's 4 particles, 8 bits each (<= 64)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const int64_t i = (group << 2) + e;
-        unsigned cells = 0;
-        DirectRec rec;
-        if (active && i >= lo && i < hi) {
-            const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
-            if (!p.keep) {
-                ++n_culled;
-            } else {
-                int j0, j1, k0, k1;
-                pixel_range(p.px0, p.px1, a.R, j0, j1);
-                pixel_range(p.py0, p.py1, a.R, k0, k1);
-                if (j1 < j0 || k1 < k0) {
-                    ++n_direct;                   // no pixel centre covered (sub-pixel or off-screen): nothing to add
-                } else {
-                    const float hh = hs[e] * hs[e];
-                    const float v0 = w0s[e] / hh;
-                    float v1, v2 = 0.0f;
-                    if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] / hh; v2 = w2s[e] / hh; }
-                    else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
-                    else v1 = w1s[e];
-                    if (p.wpx <= DIRECT_MAX_WPX && j1 - j0 < K1_MAX_SPAN && k1 - k0 < K1_MAX_SPAN) {
-                        ++n_direct;
-                        const int cj0 = j0 >> CELL_SHIFT, cj1 = j1 >> CELL_SHIFT;
-                        const unsigned ncj = (unsigned)(cj1 - cj0 + 1);
-                        cells = ncj * (unsigned)(k1 - k0 + 1);
-                        rec.px0 = p.px0; rec.py1 = p.py1; rec.inv = 1.0f / p.wpx;
-                        rec.v0 = v0; rec.v1 = v1; rec.v2 = v2;
-                        rec.cjk = (unsigned)cj0 | ((unsigned)k0 << 16);
-                        rec.jj = (unsigned)j0 | ((unsigned)j1 << 16);
-                        rec.ncj = ncj;
-                        rec.magic = (65536u + ncj - 1u) / ncj;
-                        rec.pad = 0u;
-                    } else {
-                        ++n_deferred;
-                        const unsigned slot = atomicAdd(&a.counters->q_count, 1u);
-                        if (slot < a.queue_cap) {
-                            float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
-                            q[0] = make_float4(p.px0, p.px1, p.py0, p.py1);
-                            q[1] = make_float4(p.wpx, v0, v1, v2);
-                        }
-                    }
-                }
+        if (e < e_first || e >= e_last) continue;
+        const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
+        if (!p.keep) { ++n_culled; continue; }
+        int j0, j1, k0, k1;
+        pixel_range(p.px0, p.px1, a.R, j0, j1);
+        pixel_range(p.py0, p.py1, a.R, k0, k1);
+        if (j1 < j0 || k1 < k0) { ++n_direct; continue; }     // no pixel centre covered (sub-pixel or off-screen)
+        const float rhh = 1.0f / (hs[e] * hs[e]);
+        const float v0 = w0s[e] * rhh;
+        float v1, v2 = 0.0f;
+        if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] * rhh; v2 = w2s[e] * rhh; }
+        else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
+        else v1 = w1s[e];
+        if (p.wpx <= DIRECT_MAX_WPX && j1 - j0 < K1_MAX_SPAN && k1 - k0 < K1_MAX_SPAN) {
+            ++n_direct;
+            const int cj0 = j0 >> CELL_SHIFT;
+            const unsigned ncj = (unsigned)((j1 >> CELL_SHIFT) - cj0 + 1);
+            cells4 |= (ncj * (unsigned)(k1 - k0 + 1)) << (8 * e);
+            DirectRec &r = s_rec[warp][e * 32 + lane];      // slot e*32+lane: conflict-free 128-bit stores
+            *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.py1, 1.0f / p.wpx, v0);
+            *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)),
+                                                              __uint_as_float((unsigned)j0 | ((unsigned)j1 << 16)));
+            r.ncj = ncj;
+            r.magic = c_magic[ncj];
+        } else {
+            ++n_deferred;
+            const unsigned slot = atomicAdd(&a.counters->q_count, 1u);
+            if (slot < a.queue_cap) {
+                float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
+                q[0] = make_float4(p.px0, p.px1, p.py0, p.py1);
+                q[1] = make_float4(p.wpx, v0, v1, v2);
             }
         }
-        // warp-wide exclusive prefix of the cell counts, compaction rank of the records
-        unsigned incl = cells;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        const unsigned have = __ballot_sync(0xffffffffu, cells > 0);
-        has_rec[e] = cells > 0;
-        head_off[e] = run_cells + incl - cells;
-        if (cells > 0) {
-            rec.off = head_off[e];
-            s_rec[warp][run_recs + __popc(have & lt_mask)] = rec;
-        }
-        run_cells += total;
-        run_recs += __popc(have);
     }
 
-    // ---- phase B: flattened (particle, cell) list ------------------------------------------------------------
-    const unsigned T = run_cells;
+    // one packed inclusive scan: low 16 bits = cells, high 16 bits = non-empty records
+    const unsigned c0 = cells4 & 0xffu, c1 = (cells4 >> 8) & 0xffu, c2 = (cells4 >> 16) & 0xffu, c3 = cells4 >> 24;
+    const unsigned lane_cells = c0 + c1 + c2 + c3;
+    const unsigned lane_recs = (c0 != 0u) + (c1 != 0u) + (c2 != 0u) + (c3 != 0u);
+    unsigned incl = lane_cells | (lane_recs << 16);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned T = total & 0xffffu;
     const unsigned n_words = (T + 31u) >> 5;
     for (unsigned wi = lane; wi < n_words; wi += 32) s_bits[warp][wi] = 0u;
     __syncwarp();
+    {
+        unsigned off = (incl & 0xffffu) - lane_cells, rank = (incl >> 16) - lane_recs;
+        const unsigned cs[4] = {c0, c1, c2, c3};
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-        if (has_rec[e]) atomicOr(&s_bits[warp][head_off[e] >> 5], 1u << (head_off[e] & 31u));
+        for (int e = 0; e < 4; ++e) {
+            if (cs[e]) {
+                s_rec[warp][e * 32 + lane].off = off;
+                s_slot[warp][rank] = (unsigned char)(e * 32 + lane);
+                atomicOr(&s_bits[warp][off >> 5], 1u << (off & 31u));
+                off += cs[e];
+                ++rank;
+            }
+        }
+    }
     __syncwarp();
 
-    unsigned rec_base = 0, n_reds = 0;
+    // ---- phase B: flattened (particle, cell) list ------------------------------------------------------------
+    unsigned rec_base = 0;
     for (unsigned wi = 0; wi < n_words; ++wi) {
         const unsigned word = s_bits[warp][wi];
         const unsigned t = (wi << 5) + lane;
-        const unsigned ridx = rec_base + __popc(word & (lt_mask | (1u << lane))) - 1u;
+        const unsigned rk = rec_base + __popc(word & (lt_mask | (1u << lane))) - 1u;
         rec_base += __popc(word);
         if (t < T) {
-            const DirectRec &r = s_rec[warp][ridx];
+            const DirectRec &r = s_rec[warp][s_slot[warp][rk]];
             const float4 ra = *reinterpret_cast<const float4 *>(&r.px0);      // px0 py1 inv v0
             const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk jj
             const uint4 rc = *reinterpret_cast<const uint4 *>(&r.off);        // off ncj magic pad
@@ -343,53 +349,51 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
             const unsigned local = t - rc.x;
             const unsigned dk = (local * rc.z) >> 16;
             const unsigned dc = local - dk * rc.y;
-            const int k = (int)(cjk >> 16) + (int)dk;
-            const int cj = (int)(cjk & 0xffffu) + (int)dc;
-            const int j0 = (int)(jj & 0xffffu), j1 = (int)(jj >> 16);
+            const unsigned k = (cjk >> 16) + dk;
+            const unsigned cj = (cjk & 0xffffu) + dc;
             const float fy = (float)k + 0.5f;
+            const unsigned pix = k * (unsigned)a.R + cj * CELL_W;             // R <= 32768: fits 32 bits
             if (CELL_W == 1) {
                 const float K = sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)cj + 0.5f, fy);
                 if (MODE == TSPLAT_MODE_RGB || K != 0.0f) {          // adding +0 is a no-op; RGB still counts fragments
-                    red_pixel<MODE>(a.image, (size_t)k * a.R + cj, K, ra.w, rb.x, rb.y);
-                    ++n_reds;
+                    red_pixel<MODE>(a.image, (size_t)pix, K, ra.w, rb.x, rb.y);
                 }
             } else {
+                const unsigned j0 = jj & 0xffffu, j1 = jj >> 16;
                 float Ks[CELL_W];
                 bool any = false;
 #pragma unroll
                 for (int c = 0; c < CELL_W; ++c) {
-                    const int j = cj * CELL_W + c;
+                    const unsigned j = cj * CELL_W + c;
                     const bool in = (j >= j0) && (j <= j1);
                     Ks[c] = in ? sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)j + 0.5f, fy) : 0.0f;
                     any |= (Ks[c] != 0.0f);
                 }
                 if (any) {
-                    ++n_reds;
-                    const size_t pix = (size_t)k * a.R + (size_t)cj * CELL_W;
                     if (MODE == TSPLAT_MODE_DENSITY) {
                         atomicAdd(reinterpret_cast<float4 *>(a.image + pix),
                                   make_float4(Ks[0] * ra.w, Ks[1] * ra.w, Ks[2 % CELL_W] * ra.w, Ks[3 % CELL_W] * ra.w));
                     } else {                                  // two pixels x (val, val * q|cz)
                         const float a0 = Ks[0] * ra.w, a1 = Ks[1] * ra.w;
-                        atomicAdd(reinterpret_cast<float4 *>(a.image + 2 * pix), make_float4(a0, a0 * rb.x, a1, a1 * rb.x));
+                        atomicAdd(reinterpret_cast<float4 *>(a.image + 2 * (size_t)pix), make_float4(a0, a0 * rb.x, a1, a1 * rb.x));
                     }
                 }
             }
         }
     }
 
-    // block-aggregated statistics
-    if (n_culled) atomicAdd(&s_cnt[0], n_culled);
-    if (n_direct) atomicAdd(&s_cnt[1], n_direct);
-    if (n_deferred) atomicAdd(&s_cnt[2], n_deferred);
-    for (int d = 16; d > 0; d >>= 1) n_reds += __shfl_down_sync(0xffffffffu, n_reds, d);
-    if (lane == 0 && n_reds) atomicAdd(&s_cnt[3], n_reds);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_cnt[0]) atomicAdd(&a.counters->culled, (unsigned long long)s_cnt[0]);
-        if (s_cnt[1]) atomicAdd(&a.counters->direct, (unsigned long long)s_cnt[1]);
-        if (s_cnt[3]) atomicAdd(&a.counters->reds, (unsigned long long)s_cnt[3]);
+    // warp-aggregated statistics: three global REDs per warp, spread over 32 counter slots to avoid same-address
+    // serialisation in the L2 (tsplat_get_stats sums the slots)
+    unsigned packed = n_culled | (n_direct << 8) | (n_deferred << 16);        // each <= 4 per lane, <= 128 per warp
+    for (int d = 16; d > 0; d >>= 1) packed += __shfl_down_sync(0xffffffffu, packed, d);
+#ifndef TSPLAT_NO_STATS
+    if (lane == 0) {
+        StatSlot *slot = a.counters->slots + ((blockIdx.x * K1_WARPS + warp) & (STAT_SLOTS - 1));
+        const unsigned long long cd = (unsigned long long)(packed & 0xffu) | ((unsigned long long)((packed >> 8) & 0xffu) << 32);
+        if (cd) atomicAdd(&slot->culled_direct, cd);
+        if (T) atomicAdd(&slot->reds, (unsigned long long)T);   // cells walked = vector REDs issued (minus all-zero cells)
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -405,33 +409,50 @@ struct QueueArgs {
     int R;
 };
 
+constexpr float COOP_MIN_WPX = 48.0f;        // above this a record is splatted by a whole CTA, below by one warp
+
+template <int MODE>
+__device__ __forceinline__ void atomic_splat_rows(const QueueArgs &a, const float *s_lut, const float4 q0, const float4 q1,
+                                                  int row_first, int row_step, int lane)
+{
+    const float px0 = q0.x, px1 = q0.y, py0 = q0.z, py1 = q0.w, wpx = q1.x;
+    const float inv = 1.0f / wpx;
+    int j0, j1, k0, k1;
+    pixel_range(px0, px1, a.R, j0, j1);
+    pixel_range(py0, py1, a.R, k0, k1);
+    for (int k = k0 + row_first; k <= k1; k += row_step) {
+        const float fy = (float)k + 0.5f;
+        for (int j = j0 + lane; j <= j1; j += 32) {
+            const float fx = (float)j + 0.5f;
+            const float K = sample_lut(s_lut, wpx, inv, px0, py1, fx, fy);
+            if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;
+            red_pixel<MODE>(a.image, (size_t)k * a.R + j, K, q1.y, q1.z, q1.w);
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_queue_atomic(const QueueArgs a)
 {
     __shared__ float s_lut[LUT_TOTAL];
     const unsigned count = min(*a.count, a.cap);
-    if (blockIdx.x >= count) return;
+    if (blockIdx.x >= count) return;      // neither pass has work for this CTA
     for (int i = threadIdx.x; i < LUT_TOTAL; i += blockDim.x) s_lut[i] = a.lut[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // pass 1: one warp per record (modest footprints)
+    for (unsigned w = blockIdx.x * 8u + warp; w < count; w += gridDim.x * 8u) {
+        const unsigned idx = a.indices ? a.indices[w] : w;
+        const float4 q1 = reinterpret_cast<const float4 *>(a.queue + idx)[1];
+        if (q1.x > COOP_MIN_WPX) continue;
+        atomic_splat_rows<MODE>(a, s_lut, reinterpret_cast<const float4 *>(a.queue + idx)[0], q1, 0, 1, lane);
+    }
+    // pass 2: one CTA per record (big footprints), warps interleave rows
     for (unsigned w = blockIdx.x; w < count; w += gridDim.x) {
         const unsigned idx = a.indices ? a.indices[w] : w;
-        const float4 q0 = reinterpret_cast<const float4 *>(a.queue + idx)[0];
         const float4 q1 = reinterpret_cast<const float4 *>(a.queue + idx)[1];
-        const float px0 = q0.x, px1 = q0.y, py0 = q0.z, py1 = q0.w, wpx = q1.x;
-        const float inv = 1.0f / wpx;
-        int j0, j1, k0, k1;
-        pixel_range(px0, px1, a.R, j0, j1);
-        pixel_range(py0, py1, a.R, k0, k1);
-        for (int k = k0 + warp; k <= k1; k += 8) {
-            const float fy = (float)k + 0.5f;
-            for (int j = j0 + lane; j <= j1; j += 32) {
-                const float fx = (float)j + 0.5f;
-                const float K = sample_lut(s_lut, wpx, inv, px0, py1, fx, fy);
-                if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;
-                red_pixel<MODE>(a.image, (size_t)k * a.R + j, K, q1.y, q1.z, q1.w);
-            }
-        }
+        if (!(q1.x > COOP_MIN_WPX)) continue;
+        atomic_splat_rows<MODE>(a, s_lut, reinterpret_cast<const float4 *>(a.queue + idx)[0], q1, warp, 8, lane);
     }
 }
 
@@ -566,6 +587,10 @@ __global__ void __launch_bounds__(1024) k_bin_scan(const BinArgs a)
     __shared__ unsigned s_val[CHUNK];            // tile counts of the current chunk (coalesced staging)
     __shared__ unsigned s_cnt[1024], s_seg[1024];
     unsigned carry_c = 0, carry_g = 0;           // running totals (identical in every thread)
+    if (a.counters->pair_total == 0u) {          // nothing was routed to the tiles (e.g. small queue -> atomic path)
+        if (threadIdx.x == 0) { a.counters->n_segments = 0u; a.counters->work_counter = 0u; }
+        return;
+    }
     for (int c0 = 0; c0 < a.nt; c0 += CHUNK) {
         const int n = min(CHUNK, a.nt - c0);
         __syncthreads();
@@ -1442,6 +1467,9 @@ extern "C" int tsplat_get_stats(tsplat_ctx *c, tsplat_stats *out)
     Counters h;
     CUDA_TRY(cudaStreamSynchronize(c->last_stream));
     CUDA_TRY(cudaMemcpy(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < STAT_SLOTS; ++i) {
+        h.culled += h.slots[i].culled_direct & 0xffffffffull; h.direct += h.slots[i].culled_direct >> 32; h.reds += h.slots[i].reds;
+    }
     out->particles_culled = (int64_t)h.culled;
     out->particles_direct = (int64_t)h.direct;
     out->particles_tiled = (int64_t)h.tiled;

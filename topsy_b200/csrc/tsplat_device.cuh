@@ -57,15 +57,13 @@ __device__ __forceinline__ Proj project(float x, float y, float z, float h, cons
 }
 
 // Integer pixel ranges [lo, hi] such that lo <= j <= hi  <=>  (j + 0.5f >= e0) && (j + 0.5f < e1), clipped to
-// [0, R-1].  The ceil form is equivalent to the comparison form for every j inside the image
-// (tests/test_oracle_golden.py::test_ceil_bounds_equal_comparisons checks the fp32 corner cases on the CPU).
+// [0, R-1] (empty ranges come out as lo > hi).  The ceil form is equivalent to the comparison form for every j inside
+// the image (tests/test_oracle_golden.py::test_ceil_bounds_equal_comparisons checks the fp32 corner cases on the CPU).
+// cvt.rpi.s32.f32 saturates and maps NaN to 0, so no float clamps are needed.
 __device__ __forceinline__ void pixel_range(float e0, float e1, int R, int &lo, int &hi)
 {
-    const float l = fmaxf(ceilf(e0 - 0.5f), 0.0f);
-    const float h = fminf(ceilf(e1 - 0.5f) - 1.0f, (float)(R - 1));
-    // l > h (including NaN-free huge values) -> empty
-    lo = (l <= (float)(R - 1)) ? (int)l : R;
-    hi = (h >= 0.0f) ? (int)h : -1;
+    lo = min(max(__float2int_ru(e0 - 0.5f), 0), R);
+    hi = min(max(__float2int_ru(e1 - 0.5f), 0), R) - 1;
 }
 
 // Kernel value for a quad of width wpx (inv = 1/wpx) at pixel centre (fx, fy).  `lut` holds all four levels.

@@ -42,6 +42,8 @@ WORKLOADS = {
     "c2": Workload("c2", "10M dark-matter particles, 1024^2 density projection + log colormap", 10_000_000, 1024, "density", 1.0),
     "c3": Workload("c3", "50M gas particles, 2048^2 density-weighted temperature (two-channel)", 50_000_000, 2048, "weighted", 1.0),
     "c4": Workload("c4", "100M star particles, 2048^2 RGB three-band render", 100_000_000, 2048, "rgb", 0.1),
+    "c4s": Workload("c4s", "100M star particles with sub-pixel footprints (h_factor 0.03), 2048^2 RGB three-band render", 100_000_000, 2048,
+                    "rgb", 0.03),
     "c5": Workload("c5", "1B particles over 8 GPUs (125M per GPU), 4096^2 density projection + image sum-reduce", 125_000_000, 4096,
                    "density", 0.1),
 }
