@@ -411,48 +411,51 @@ struct QueueArgs {
 
 constexpr float COOP_MIN_WPX = 48.0f;        // above this a record is splatted by a whole CTA, below by one warp
 
+// Splat one queue record with atomics.  The (row, column) grid of covered pixels is flattened over the `nthreads`
+// cooperating threads (a warp or a whole CTA), so narrow footprints still fill all lanes.  The kernel LUT is read
+// through the read-only L1 path (22 KB, hot): no shared-memory staging, no barrier before the first RED.
 template <int MODE>
-__device__ __forceinline__ void atomic_splat_rows(const QueueArgs &a, const float *s_lut, const float4 q0, const float4 q1,
-                                                  int row_first, int row_step, int lane)
+__device__ __forceinline__ void atomic_splat_record(const QueueArgs &a, const float4 q0, const float4 q1, unsigned tid,
+                                                    unsigned nthreads)
 {
     const float px0 = q0.x, px1 = q0.y, py0 = q0.z, py1 = q0.w, wpx = q1.x;
     const float inv = 1.0f / wpx;
     int j0, j1, k0, k1;
     pixel_range(px0, px1, a.R, j0, j1);
     pixel_range(py0, py1, a.R, k0, k1);
-    for (int k = k0 + row_first; k <= k1; k += row_step) {
-        const float fy = (float)k + 0.5f;
-        for (int j = j0 + lane; j <= j1; j += 32) {
-            const float fx = (float)j + 0.5f;
-            const float K = sample_lut(s_lut, wpx, inv, px0, py1, fx, fy);
-            if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;
-            red_pixel<MODE>(a.image, (size_t)k * a.R + j, K, q1.y, q1.z, q1.w);
-        }
+    if (j1 < j0 || k1 < k0) return;
+    const unsigned ncols = (unsigned)(j1 - j0 + 1), total = ncols * (unsigned)(k1 - k0 + 1);
+    const float rcols = 1.0f / (float)ncols;
+    for (unsigned t = tid; t < total; t += nthreads) {
+        unsigned dk = (unsigned)((float)t * rcols);               // t / ncols up to rounding; fixed below
+        unsigned dj = t - dk * ncols;
+        if ((int)dj < 0) { --dk; dj += ncols; } else if (dj >= ncols) { ++dk; dj -= ncols; }
+        const int k = k0 + (int)dk, j = j0 + (int)dj;
+        const float K = sample_lut(a.lut, wpx, inv, px0, py1, (float)j + 0.5f, (float)k + 0.5f);
+        if (MODE != TSPLAT_MODE_RGB && K == 0.0f) continue;
+        red_pixel<MODE>(a.image, (size_t)k * a.R + j, K, q1.y, q1.z, q1.w);
     }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_queue_atomic(const QueueArgs a)
 {
-    __shared__ float s_lut[LUT_TOTAL];
     const unsigned count = min(*a.count, a.cap);
     if (blockIdx.x >= count) return;      // neither pass has work for this CTA
-    for (int i = threadIdx.x; i < LUT_TOTAL; i += blockDim.x) s_lut[i] = a.lut[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // pass 1: one warp per record (modest footprints)
     for (unsigned w = blockIdx.x * 8u + warp; w < count; w += gridDim.x * 8u) {
         const unsigned idx = a.indices ? a.indices[w] : w;
-        const float4 q1 = reinterpret_cast<const float4 *>(a.queue + idx)[1];
+        const float4 q1 = __ldg(reinterpret_cast<const float4 *>(a.queue + idx) + 1);
         if (q1.x > COOP_MIN_WPX) continue;
-        atomic_splat_rows<MODE>(a, s_lut, reinterpret_cast<const float4 *>(a.queue + idx)[0], q1, 0, 1, lane);
+        atomic_splat_record<MODE>(a, __ldg(reinterpret_cast<const float4 *>(a.queue + idx)), q1, lane, 32u);
     }
-    // pass 2: one CTA per record (big footprints), warps interleave rows
+    // pass 2: one CTA per record (big footprints)
     for (unsigned w = blockIdx.x; w < count; w += gridDim.x) {
         const unsigned idx = a.indices ? a.indices[w] : w;
-        const float4 q1 = reinterpret_cast<const float4 *>(a.queue + idx)[1];
+        const float4 q1 = __ldg(reinterpret_cast<const float4 *>(a.queue + idx) + 1);
         if (!(q1.x > COOP_MIN_WPX)) continue;
-        atomic_splat_rows<MODE>(a, s_lut, reinterpret_cast<const float4 *>(a.queue + idx)[0], q1, warp, 8, lane);
+        atomic_splat_record<MODE>(a, __ldg(reinterpret_cast<const float4 *>(a.queue + idx)), q1, threadIdx.x, 256u);
     }
 }
 
