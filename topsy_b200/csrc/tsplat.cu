@@ -154,13 +154,45 @@ struct ProjectArgs {
     RangeTable table;            // used when table.n > 0
 };
 
-// streaming 128-bit load of 4 consecutive particles of one SoA array (read once: bypass L1 allocation)
-__device__ __forceinline__ float4 ld4(const float *__restrict__ p, int64_t group)
+// L2 residency control: the particle stream is read exactly once (evict_first), the accumulation image is re-hit by
+// every particle (evict_last), so the streaming reads must not push image lines out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// streaming 128-bit load of 4 consecutive particles of one SoA array (read once: no L1 allocation, L2 evict-first)
+__device__ __forceinline__ float4 ld4(const float *__restrict__ p, int64_t group, uint64_t pol)
 {
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(reinterpret_cast<const float4 *>(p) + group));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(reinterpret_cast<const float4 *>(p) + group), "l"(pol));
     return r;
+}
+
+__device__ __forceinline__ void red_v4(float *addr, float a, float b, float c, float d, uint64_t pol)
+{
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void red_v2(float *addr, float a, float b, uint64_t pol)
+{
+    asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(addr), "f"(a), "f"(b), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void red_v1(float *addr, float a, uint64_t pol)
+{
+    asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(addr), "f"(a), "l"(pol) : "memory");
 }
 
 __device__ __forceinline__ float4 ld4_tail(const float *__restrict__ p, int64_t base, int64_t left)
@@ -211,6 +243,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     __shared__ unsigned char s_slot[K1_WARPS][K1_RECS];      // rank among non-empty records -> record slot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float2 lut_pair = __ldg(reinterpret_cast<const float2 *>(a.lut + lut_offset(3)) + lane);
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_image = l2_policy_evict_last();
     const float *s_lut8 = s_lut8w[warp];
     const unsigned lt_mask = (1u << lane) - 1u;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,9 +277,9 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         const int64_t base = group << 2;
         if (active) {
             if (base + 4 <= a.n_total) {
-                X = ld4(a.x, group); Y = ld4(a.y, group); Z = ld4(a.z, group); H = ld4(a.h, group); W0 = ld4(a.w0, group);
-                if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4(a.w1, group);
-                if (MODE == TSPLAT_MODE_RGB) W2 = ld4(a.w2, group);
+                X = ld4(a.x, group, pol_stream); Y = ld4(a.y, group, pol_stream); Z = ld4(a.z, group, pol_stream); H = ld4(a.h, group, pol_stream); W0 = ld4(a.w0, group, pol_stream);
+                if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4(a.w1, group, pol_stream);
+                if (MODE == TSPLAT_MODE_RGB) W2 = ld4(a.w2, group, pol_stream);
             } else {                              // partial last group of the buffer: element-wise, in bounds
                 const int64_t left = a.n_total - base;
                 X = ld4_tail(a.x, base, left); Y = ld4_tail(a.y, base, left); Z = ld4_tail(a.z, base, left);
@@ -355,8 +388,12 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
             const unsigned pix = k * (unsigned)a.R + cj * CELL_W;             // R <= 32768: fits 32 bits
             if (CELL_W == 1) {
                 const float K = sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)cj + 0.5f, fy);
-                if (MODE == TSPLAT_MODE_RGB || K != 0.0f) {          // adding +0 is a no-op; RGB still counts fragments
-                    red_pixel<MODE>(a.image, (size_t)pix, K, ra.w, rb.x, rb.y);
+                if (MODE == TSPLAT_MODE_RGB) {                       // RGB counts fragments even where K == 0
+                    red_v4(a.image + 4 * (size_t)pix, ra.w * K, rb.x * K, rb.y * K, 1.0f, pol_image);
+                } else if (K != 0.0f) {                              // adding +0 is a no-op
+                    const float val = K * ra.w;
+                    if (MODE == TSPLAT_MODE_DENSITY) red_v1(a.image + pix, val, pol_image);
+                    else red_v2(a.image + 2 * (size_t)pix, val, val * rb.x, pol_image);
                 }
             } else {
                 const unsigned j0 = jj & 0xffffu, j1 = jj >> 16;
@@ -371,11 +408,10 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                 }
                 if (any) {
                     if (MODE == TSPLAT_MODE_DENSITY) {
-                        atomicAdd(reinterpret_cast<float4 *>(a.image + pix),
-                                  make_float4(Ks[0] * ra.w, Ks[1] * ra.w, Ks[2 % CELL_W] * ra.w, Ks[3 % CELL_W] * ra.w));
+                        red_v4(a.image + pix, Ks[0] * ra.w, Ks[1] * ra.w, Ks[2 % CELL_W] * ra.w, Ks[3 % CELL_W] * ra.w, pol_image);
                     } else {                                  // two pixels x (val, val * q|cz)
                         const float a0 = Ks[0] * ra.w, a1 = Ks[1] * ra.w;
-                        atomicAdd(reinterpret_cast<float4 *>(a.image + 2 * (size_t)pix), make_float4(a0, a0 * rb.x, a1, a1 * rb.x));
+                        red_v4(a.image + 2 * (size_t)pix, a0, a0 * rb.x, a1, a1 * rb.x, pol_image);
                     }
                 }
             }
