@@ -116,6 +116,10 @@ def camera_for(workload):
 
 MODE_ID = {"density": 0, "weighted": 1, "rgb": 2}
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_project_splat, one launch = 2^25 particles),
+# from the committed ncu capture; None where no capture exists for the workload
+NCU_TRAFFIC_PER_LAUNCH = {"c4": 1.055e9}
+
 
 def export_blocks(n, block=2 ** 25):
     """EXPORT-frame blocks of RenderProgression.get_block (progressive_render.py:55-64)."""
@@ -361,7 +365,11 @@ def run_ours(args):
             "phases_ms": {"splat": splat_ms_max, "reduce_and_colormap": present_ms},
             "roofline": {"bound": "hbm", "kernel": "k_project_splat (+ deferred queue kernels) per frame",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_frame": bytes_alg, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_frame": bytes_alg,
+                         "algorithmic_bytes_per_launch": min(n, 2 ** 25) * wl.bytes_per_particle,
+                         "traffic": NCU_TRAFFIC_PER_LAUNCH.get(wl.name),
+                         "traffic_source": "profiles/r01/k1_c4_dram_traffic_v5.txt (ncu dram__bytes_read+write per 2^25-particle launch)"
+                         if wl.name in NCU_TRAFFIC_PER_LAUNCH else None,
                          "bytes_per_particle": wl.bytes_per_particle},
             "atomic_roofline": {"bound": "vector RED issue rate (SM-side L1TEX limit; profiles/r01/atomics_bench_b200.txt)",
                                 "direct_vector_reds_per_frame": int(st["direct_vector_reds"]),
