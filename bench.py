@@ -34,8 +34,8 @@ UNIT = "Gparticles/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=None, help="override particles per GPU (debug)")
@@ -49,7 +49,12 @@ def parse_args():
 # helpers
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi is started before the warm-up (it needs ~100 ms to come up), loops every 20 ms, and every line is
+    stamped on receipt; ``stop(t0, t1)`` keeps the samples that fall inside the timed region [t0, t1].  If the region
+    is shorter than one sampling period the samples of the enclosing loaded window (warm-up + timed) are used and the
+    result says so."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -62,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -71,31 +76,47 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=3.0):
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.005)
+
+    def stop(self, t0=None, t1=None, t_loaded=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, smax, reasons, power = [], [], set(), []
+            for _, ln in rows:
+                f = [t.strip() for t in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, smax, reasons, power
+
+        window = "timed region"
+        rows = [r for r in self.lines if t0 is None or (t0 <= r[0] <= t1)]
+        if not rows and t_loaded is not None:
+            rows = [r for r in self.lines if t_loaded <= r[0] <= t1 + 0.03]
+            window = "warm-up + timed region (timed region shorter than the 20 ms sampling period)"
+        sm, smax, reasons, power = parse(rows)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def measured_peak():
@@ -274,12 +295,14 @@ def run_ours(args):
         vmin, vmax = 0.0, 1.0
     params.vmin, params.vmax = vmin, vmax
 
-    for _ in range(args.warmup):
-        frame()
-    launches0 = eng.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    t_loaded = time.perf_counter()
+    for _ in range(args.warmup):
+        frame()
+    launches0 = eng.stats()["kernel_launches"]
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     for e in evs:
         e[2] = e[3]
@@ -293,8 +316,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
+    clocks = sampler.stop(t_wall0, t_wall1, t_loaded) if rank == 0 else None
     st = eng.stats()
     launches = st["kernel_launches"] - launches0
     total_ms = evs[0][0].elapsed_time(evs[-1][3])
