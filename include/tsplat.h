@@ -135,6 +135,13 @@ int tsplat_reduce_colormap(tsplat_ctx *ctx, const float *const *peer_images, int
                            int row0, int nrows, const tsplat_colormap_params *params, const float *lut,
                            int lut_w, int lut_h, void *out, int out_fmt, float *sum_out, void *stream);
 
+/* Replaces PeriodicSPH's accumulation pass (periodic_sph.py:59-88, overlay.py, shaders/overlay.wgsl): dst (R x R x
+ * channels, device) = sum over n <= 128 replicas of weights[i] * src sampled bilinearly at the pixel shifted by the
+ * clip-space offset (offsets_xy[2i], offsets_xy[2i+1]); a replica contributes only inside its own [-1,1]^2 + offset
+ * quad.  offsets_xy / weights are HOST arrays. */
+int tsplat_periodic_accumulate(tsplat_ctx *ctx, const float *src, float *dst, int channels, const float *offsets_xy,
+                               const float *weights, int n, void *stream);
+
 /* out[i] = a[i] + b[i] * scale, used by PeriodicSPH-style accumulation and by tests (device pointers). */
 int tsplat_image_axpy(tsplat_ctx *ctx, float *dst, const float *src, float scale, int64_t n, void *stream);
 

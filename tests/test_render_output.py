@@ -61,6 +61,35 @@ def test_sph_output(vis, goldens):
     assert (test / expect).std() < 0.015
 
 
+def test_periodic_sph_output(goldens):
+    vis2 = topsy.test(1000, render_resolution=200, canvas_class=offscreen.VisualizerCanvas, periodic_tiling=True)
+    vis2.scale = 200.0
+    vis2.render_sph(DrawReason.EXPORT)
+    result = vis2.get_sph_image()
+    npt.assert_allclose(result[::20, ::20].flatten(), goldens["test_periodic_sph_output__expect"], rtol=1e-1)
+    assert vis2.get_sph_presentation_image().shape == (200, 200, 4)
+
+
+def test_periodic_accumulate_matches_oracle():
+    """K7 against the numpy restatement of the replica sum, rotated view with fractional pixel shifts."""
+    from oracle import topsy_oracle as o
+    from topsy_b200 import periodic_sph
+    vis2 = topsy.test(1000, render_resolution=200, canvas_class=offscreen.VisualizerCanvas, periodic_tiling=True)
+    vis2.scale = 130.0
+    vis2.rotate(0.3, 0.2)
+    vis2.render_sph(DrawReason.EXPORT)
+    base = vis2._sph._current_image().cpu().numpy().astype(np.float64)
+    offs, wts = o.periodic_instances(vis2.rotation_matrix, 100.0 / 130.0)
+    offs2, wts2 = periodic_sph.replica_offsets_and_weights(vis2.rotation_matrix, 100.0 / 130.0)
+    assert len(wts) == len(wts2)
+    order = np.lexsort(np.round(offs.T, 4)); order2 = np.lexsort(np.round(offs2.T, 4))
+    npt.assert_allclose(offs[order], offs2[order2], atol=1e-6); npt.assert_allclose(wts[order], wts2[order2], atol=1e-6)
+    want = o.periodic_accumulate(base, offs, wts)
+    got = vis2._sph._current_periodic_image().cpu().numpy()
+    big = want[..., 0] > 1e-6 * want[..., 0].max()
+    npt.assert_allclose(got[..., 0][big], want[..., 0][big], rtol=2e-4)
+
+
 def test_rotated_sph_output(vis):
     vis.draw(reason=DrawReason.EXPORT)
     unrotated = vis.get_sph_image()

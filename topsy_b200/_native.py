@@ -60,6 +60,7 @@ _SIGNATURES = {
                                _i32, _vp]),
     "tsplat_reduce_colormap": (_i32, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i32, _i32, ctypes.POINTER(ColormapParams), _vp,
                                       _i32, _i32, _vp, _i32, _vp, _vp]),
+    "tsplat_periodic_accumulate": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "tsplat_image_axpy": (_i32, [_vp, _vp, _vp, _f, _i64, _vp]),
     "tsplat_cell_layout_work_bytes": (_i64, [_i64, _i32]),
     "tsplat_cell_layout": (_i32, [_i32, _vp, _i64, _i32, ctypes.c_double, ctypes.c_double, _i32, _vp, _vp, _vp, _vp,

@@ -1057,6 +1057,54 @@ __global__ void __launch_bounds__(256) k_reduce_colormap(const ReduceArgs a)
     if (a.out) store_rgba(a.out, pix, a.out_fmt, colormap_value(v, a.p, a.lut, a.lut_w, a.lut_h));
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K7: periodic tiling -- out = sum_i w_i * image shifted by offset_i (reference: periodic_sph.py:16-88 draws the SPH
+// texture as <= 125 instanced quads through overlay.wgsl with a linear sampler and ONE/ONE blending)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MAX_REPLICAS = 128;             // Overlay.MAX_INSTANCES (overlay.py:21)
+
+struct PeriodicArgs {
+    const float *src;
+    float *dst;
+    int res, channels, n;
+    float ox[MAX_REPLICAS], oy[MAX_REPLICAS], w[MAX_REPLICAS];
+};
+
+__global__ void __launch_bounds__(256) k_periodic_accumulate(const PeriodicArgs a)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (j >= a.res) return;
+    const float Rf = (float)a.res;
+    const float X = (2.0f * (float)j + 1.0f) / Rf - 1.0f;      // pixel centre in clip space, row 0 = +y
+    const float Y = 1.0f - (2.0f * (float)k + 1.0f) / Rf;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < a.n; ++i) {
+        const float u = (X - (a.ox[i] - 1.0f)) * 0.5f;
+        const float v = ((a.oy[i] + 1.0f) - Y) * 0.5f;
+        if (!(u >= 0.0f && u < 1.0f && v > 0.0f && v <= 1.0f)) continue;       // outside this replica's quad
+        const float px = u * Rf - 0.5f, py = v * Rf - 0.5f;
+        const float ix = floorf(px), iy = floorf(py);
+        const float fx = px - ix, fy = py - iy;
+        const int x0 = min(max((int)ix, 0), a.res - 1), x1 = min(max((int)ix + 1, 0), a.res - 1);
+        const int y0 = min(max((int)iy, 0), a.res - 1), y1 = min(max((int)iy + 1, 0), a.res - 1);
+        float t00[4], t01[4], t10[4], t11[4];
+        load_pixel(a.src, a.res, a.channels, x0, y0, t00);
+        load_pixel(a.src, a.res, a.channels, x1, y0, t01);
+        load_pixel(a.src, a.res, a.channels, x0, y1, t10);
+        load_pixel(a.src, a.res, a.channels, x1, y1, t11);
+        const float wi = a.w[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float top = t00[c] + (t01[c] - t00[c]) * fx, bot = t10[c] + (t11[c] - t10[c]) * fx;
+            acc[c] += wi * (top + (bot - top) * fy);
+        }
+    }
+    const size_t pix = (size_t)k * a.res + j;
+    if (a.channels == 1) a.dst[pix] = acc[0];
+    else if (a.channels == 2) reinterpret_cast<float2 *>(a.dst)[pix] = make_float2(acc[0], acc[1]);
+    else reinterpret_cast<float4 *>(a.dst)[pix] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 __global__ void k_axpy(float *__restrict__ dst, const float *__restrict__ src, float scale, int64_t n)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -1460,6 +1508,26 @@ extern "C" int tsplat_reduce_colormap(tsplat_ctx *c, const float *const *peer_im
     a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_fmt = out_fmt; a.sum_out = sum_out;
     dim3 grid((c->R + 255) / 256, nrows);
     k_reduce_colormap<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    c->launches++;
+    c->last_stream = (cudaStream_t)stream;
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_periodic_accumulate(tsplat_ctx *c, const float *src, float *dst, int channels, const float *offsets_xy,
+                                          const float *weights, int n, void *stream)
+{
+    if (!c || !src || !dst || (n > 0 && (!offsets_xy || !weights))) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (src == dst) return set_err(TSPLAT_ERR_INVALID, "src and dst must differ");
+    if (channels != 1 && channels != 2 && channels != 4) return set_err(TSPLAT_ERR_INVALID, "channels must be 1, 2 or 4");
+    if (n < 0 || n > MAX_REPLICAS) return set_err(TSPLAT_ERR_INVALID, "replica count %d outside [0, %d]", n, MAX_REPLICAS);
+    CUDA_TRY(cudaSetDevice(c->device));
+    PeriodicArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = src; a.dst = dst; a.res = c->R; a.channels = channels; a.n = n;
+    for (int i = 0; i < n; ++i) { a.ox[i] = offsets_xy[2 * i]; a.oy[i] = offsets_xy[2 * i + 1]; a.w[i] = weights[i]; }
+    dim3 grid((c->R + 255) / 256, c->R);
+    k_periodic_accumulate<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());

@@ -58,8 +58,6 @@ class VisualizerBase:
         self._setup_device()
         self._configure_canvas_context()
         self._initialize_data_loader_and_buffers(data_loader_class, data_loader_args, data_loader_kwargs)
-        if periodic_tiling:
-            raise NotImplementedError("periodic_tiling (PeriodicSPH) is not part of the B200 hot path yet (SURVEY.md 8f)")
         self._periodic_tiling = periodic_tiling
         self._status_text = "topsy"
         self._initialize_sph_and_colormap_and_bar(colormap_name)
@@ -115,9 +113,13 @@ class VisualizerBase:
         """(Re-)create renderer, colormap and colorbar, keeping the camera (visualizer.py:122-154)."""
         old = (self._sph.rotation_matrix, self._sph.position_offset, self._sph.scale) if self._sph is not None \
             else (None, None, None)
-        sph_class = self._get_sph_class_for_render_mode(self._render_mode)
-        logger.info(f"Using {sph_class.__name__} renderer for render mode '{self._render_mode}'")
-        self._sph = sph_class(self, self._render_resolution)
+        if self._periodic_tiling:
+            from . import periodic_sph
+            self._sph = periodic_sph.PeriodicSPH(self, self._render_resolution)
+        else:
+            sph_class = self._get_sph_class_for_render_mode(self._render_mode)
+            logger.info(f"Using {sph_class.__name__} renderer for render mode '{self._render_mode}'")
+            self._sph = sph_class(self, self._render_resolution)
         self.reset_view(rotation_matrix=old[0], position_offset=old[1], scale=old[2])
         self.invalidate()
         if colormap_name is None:
