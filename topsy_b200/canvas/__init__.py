@@ -1,111 +1,128 @@
-"""Canvas layer (reference: src/topsy/canvas/__init__.py).  Only the toolkit-neutral base class and the offscreen canvas
-are part of the B200 hot path; the Qt / Jupyter front-ends of the reference are windowing code and are not provided."""
+"""Canvas layer (API of the reference's src/topsy/canvas/__init__.py).  Only the toolkit-neutral interaction logic and
+the offscreen canvas belong to the B200 hot path; the Qt / Jupyter front-ends of the reference are windowing code and
+are not provided."""
 from __future__ import annotations
 
-import copy
 import time
 
 import numpy as np
 
 from .. import config
 
+ROTATE_RADIANS_PER_PIXEL = 0.01
+WHEEL_ZOOM_DIVISOR = 1000.0
+
 
 class VisualizerCanvasBase:
-    """Mouse / keyboard semantics shared by every canvas: drag rotates, shift-drag pans, wheel zooms, double click
-    re-centres on the point under the cursor using the depth image (canvas/__init__.py:16-160)."""
+    """Interaction semantics shared by every canvas (canvas/__init__.py:16-160 of the reference):
+    drag = rotate, modifier + drag = pan, wheel = zoom, double click = re-centre on the matter under the cursor
+    (found through the depth image), keys s / r / h / w = save, autorange, home view, print the camera."""
 
     def __init__(self, *args, **kwargs):
         self._visualizer = kwargs.pop("visualizer")
-        self._last_x = 0
-        self._last_y = 0
-        self.width_physical, self.height_physical = 640, 480      # until the first resize event
+        self._pointer = (0, 0)
+        self.width_physical, self.height_physical = 640, 480      # replaced by the first resize event
         self.pixel_ratio = 1
         super().__init__(*args, **kwargs)
+        self._dispatch = {
+            'pointer_move': self._on_pointer_move,
+            'wheel': lambda ev: self.mouse_wheel(ev['dx'], ev['dy']),
+            'key_up': lambda ev: self.key_up(ev['key']),
+            'resize': lambda ev: self.resize_complete(ev['width'], ev['height'], ev['pixel_ratio']),
+            'double_click': lambda ev: self.double_click(ev['x'], ev['y']),
+            'pointer_up': lambda ev: self.release_drag(),
+        }
         self.add_event_handler(self.event_handler, "*")
 
+    # -- event plumbing -----------------------------------------------------------------------------------------
     def event_handler(self, event):
-        kind = event['event_type']
-        if kind == 'pointer_move':
-            if len(event['buttons']) > 0:
-                move = self.drag if len(event['modifiers']) == 0 else self.shift_drag
-                move(event['x'] - self._last_x, event['y'] - self._last_y)
-            self._last_x, self._last_y = event['x'], event['y']
-        elif kind == 'wheel':
-            self.mouse_wheel(event['dx'], event['dy'])
-        elif kind == 'key_up':
-            self.key_up(event['key'])
-        elif kind == 'resize':
-            self.resize_complete(event['width'], event['height'], event['pixel_ratio'])
-        elif kind == 'double_click':
-            self.double_click(event['x'], event['y'])
-        elif kind == 'pointer_up':
-            self.release_drag()
+        handler = self._dispatch.get(event['event_type'])
+        if handler is not None:
+            handler(event)
 
+    def _on_pointer_move(self, event):
+        dx, dy = event['x'] - self._pointer[0], event['y'] - self._pointer[1]
+        if event['buttons']:
+            (self.shift_drag if event['modifiers'] else self.drag)(dx, dy)
+        self._pointer = (event['x'], event['y'])
+
+    # kept for code that pokes the reference's attribute names
+    @property
+    def _last_x(self):
+        return self._pointer[0]
+
+    @property
+    def _last_y(self):
+        return self._pointer[1]
+
+    # -- gestures -----------------------------------------------------------------------------------------------
     def drag(self, dx, dy):
-        self._visualizer.rotate(dx * 0.01, dy * 0.01)
+        self._visualizer.rotate(dx * ROTATE_RADIANS_PER_PIXEL, dy * ROTATE_RADIANS_PER_PIXEL)
 
-    def _screen_to_world(self, dx, dy):
-        span = max(self.width_physical, self.height_physical)
-        shift = 2.0 * self.pixel_ratio * np.array([dx, dy, 0], dtype=np.float32) / span * self._visualizer.scale
-        return self._visualizer.rotation_matrix.T @ shift
+    def _pixels_to_world(self, right, up):
+        """Displacement in simulation coordinates of a screen-space move of (right, up) logical pixels."""
+        vis = self._visualizer
+        extent = max(self.width_physical, self.height_physical)
+        in_view = np.array([right, up, 0], dtype=np.float32) * (2.0 * self.pixel_ratio * vis.scale / extent)
+        return vis.rotation_matrix.T @ in_view
 
     def shift_drag(self, dx, dy):
-        self._visualizer.position_offset += self._screen_to_world(dx, -dy)
-        self._visualizer.display_status("centre = [{:.2f}, {:.2f}, {:.2f}]".format(*self._visualizer._sph.position_offset))
-        self._visualizer.crosshairs_visible = True
-
-    def key_up(self, key):
-        if key == 's':
-            self._visualizer.save()
-        elif key == 'r':
-            self._visualizer.colormap_autorange()
-        elif key == 'h':
-            self._visualizer.reset_view()
-        elif key == 'w':
-            offset = np.array2string(self._visualizer.position_offset, separator=",")
-            rot = np.array2string(self._visualizer.rotation_matrix, separator=",")
-            print(f".translate({offset}).transform(np.array({rot}))")
-
-    def mouse_wheel(self, delta_x, delta_y):
-        self._visualizer.scale *= np.exp(delta_y / 1000)
+        vis = self._visualizer
+        vis.position_offset += self._pixels_to_world(dx, -dy)
+        vis.display_status("centre = [{:.2f}, {:.2f}, {:.2f}]".format(*vis._sph.position_offset))
+        vis.crosshairs_visible = True
 
     def release_drag(self):
-        if self._visualizer.crosshairs_visible:
-            self._visualizer.crosshairs_visible = False
-            self._visualizer.invalidate()
+        vis = self._visualizer
+        if vis.crosshairs_visible:
+            vis.crosshairs_visible = False
+            vis.invalidate()
+
+    def mouse_wheel(self, delta_x, delta_y):
+        self._visualizer.scale *= np.exp(delta_y / WHEEL_ZOOM_DIVISOR)
+
+    def key_up(self, key):
+        vis = self._visualizer
+        actions = {'s': vis.save, 'r': vis.colormap_autorange, 'h': vis.reset_view}
+        if key in actions:
+            actions[key]()
+        elif key == 'w':
+            shift = np.array2string(vis.position_offset, separator=",")
+            turn = np.array2string(vis.rotation_matrix, separator=",")
+            print(f".translate({shift}).transform(np.array({turn}))")
 
     def resize_complete(self, width, height, pixel_ratio=1):
-        self.width_physical = int(width * pixel_ratio)
-        self.height_physical = int(height * pixel_ratio)
         self.pixel_ratio = pixel_ratio
+        self.width_physical, self.height_physical = int(width * pixel_ratio), int(height * pixel_ratio)
 
     def double_click(self, x, y):
+        """Move the clicked point to the view centre, in depth too, then animate the move (GLIDE_TIME)."""
         vis = self._visualizer
-        start = copy.copy(vis.position_offset)
-        cx = self.width_physical / (2 * self.pixel_ratio)
-        cy = self.height_physical / (2 * self.pixel_ratio)
-        vis.position_offset += self._screen_to_world(cx - x, y - cy)
-        depth = vis.get_depth_image()
-        central = depth[depth.shape[0] // 2, depth.shape[1] // 2]
-        if not np.isnan(central):
-            vis.position_offset += vis.rotation_matrix.T @ np.array([0, 0, -central], dtype=np.float32)
-        target = vis.position_offset
-        vis.position_offset = start          # the work is done; now glide there so the motion is readable
-        t0 = time.time()
+        origin = np.array(vis.position_offset, copy=True)
+        half_w = self.width_physical / (2 * self.pixel_ratio)
+        half_h = self.height_physical / (2 * self.pixel_ratio)
+        vis.position_offset += self._pixels_to_world(half_w - x, y - half_h)
+        depth_map = vis.get_depth_image()
+        depth_here = depth_map[depth_map.shape[0] // 2, depth_map.shape[1] // 2]
+        if not np.isnan(depth_here):
+            vis.position_offset += vis.rotation_matrix.T @ np.array([0, 0, -depth_here], dtype=np.float32)
+        destination = vis.position_offset
+        vis.position_offset = origin
+        began = time.time()
 
-        def ease(t):
-            w = np.arctan(5 * (t * 2 - 1)) / np.pi + 0.5
-            return (1 - w) * start + w * target
+        def blend(t):                      # smooth-step made of an arctangent, as in the reference
+            w = np.arctan(5 * (2 * t - 1)) / np.pi + 0.5
+            return origin + w * (destination - origin)
 
-        def glide():
-            t = (time.time() - t0) / config.GLIDE_TIME
-            if t > 1:
-                vis.position_offset = target
+        def step():
+            t = (time.time() - began) / config.GLIDE_TIME
+            if t <= 1:
+                self.call_later(0.0, step)
+                vis.position_offset = blend(t)
             else:
-                self.call_later(0.0, glide)
-                vis.position_offset = ease(t)
+                vis.position_offset = destination
 
-        self.call_later(1.0 / config.TARGET_FPS, glide)
+        self.call_later(1.0 / config.TARGET_FPS, step)
 
     @classmethod
     def call_later(cls, delay, fn, *args):
