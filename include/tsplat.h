@@ -142,6 +142,23 @@ int tsplat_reduce_colormap(tsplat_ctx *ctx, const float *const *peer_images, int
 int tsplat_periodic_accumulate(tsplat_ctx *ctx, const float *src, float *dst, int channels, const float *offsets_xy,
                                const float *weights, int n, void *stream);
 
+/* Device-side autorange (replaces the host read-back + np.percentile of colormap/implementation.py:381-425,
+ * :512-531, :576-588).  "content" selects what the colormap looks at: 0 = channel 0 * scale (density), 1 = channel 1 /
+ * channel 0 (weighted mean), 2 = every channel * scale (RGB maps, which include the count channel like the reference).
+ * tsplat_content_stats: finite min/max of the values and of their log10, whether any value is negative, counts.
+ * tsplat_content_select: exact order statistics (0-based ranks among the finite values, ascending) of the values or of
+ * their log10 -- a 3-pass radix select; the host interpolates percentiles from them like np.percentile.
+ * Both calls synchronise the stream (they return host values). */
+typedef struct {
+    float lin_min, lin_max, log_min, log_max;     /* NaN when there is no finite value */
+    int64_t n_finite_lin, n_finite_log;
+    int32_t any_negative;
+} tsplat_content_stats_t;
+int tsplat_content_stats(tsplat_ctx *ctx, const float *image, int res, int channels, int content, float scale,
+                         tsplat_content_stats_t *out, void *stream);
+int tsplat_content_select(tsplat_ctx *ctx, const float *image, int res, int channels, int content, float scale,
+                          int use_log, const int64_t *ranks, int n_ranks, float *out_values, void *stream);
+
 /* out[i] = a[i] + b[i] * scale, used by PeriodicSPH-style accumulation and by tests (device pointers). */
 int tsplat_image_axpy(tsplat_ctx *ctx, float *dst, const float *src, float scale, int64_t n, void *stream);
 

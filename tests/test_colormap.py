@@ -140,3 +140,35 @@ def test_presentation_resampling(device):
     assert got.shape == (64, 128, 4)
     assert (np.diff(got[32, :, 0].astype(int)) >= 0).all() and got[32, -1, 0] > got[32, 0, 0] + 100
     assert np.abs(got[10].astype(int) - got[50].astype(int)).max() <= 1     # rows identical: y is cropped, not stretched
+
+
+@pytest.mark.parametrize("kind", ["density", "weighted", "signed", "bivariate", "rgb", "rgb-hdr", "tiny"])
+def test_device_autorange_equals_host_autorange(device, kind):
+    """K8 (stats + radix select on the device) against the reference's host rule (numpy percentiles of the read-back)."""
+    rs = np.random.RandomState(11)
+    R = 160 if kind != "tiny" else 12
+    if kind.startswith("rgb"):
+        img = np.exp(rs.normal(size=(R, R, 4)) * 2).astype(np.float32)
+        img[..., 3] = rs.randint(0, 30, (R, R))
+        img[rs.uniform(size=(R, R)) < 0.05] = 0.0
+        params = {'type': 'rgb', 'hdr': kind == "rgb-hdr", 'log': True}
+        fmt = "rgba16float" if kind == "rgb-hdr" else "rgba8unorm"
+    else:
+        img = make_image(R=R, seed=21, signed=(kind in ("signed", "bivariate")))
+        params = {'type': 'bivariate' if kind == "bivariate" else 'density', 'colormap_name': 'viridis',
+                  'weighted_average': kind in ("weighted", "signed", "bivariate")}
+        fmt = "rgba8unorm"
+    scale = 2.5
+    host, _ = holder_for(device, img, params, fmt)
+    dev, _ = holder_for(device, img, params, fmt)
+    host.autorange(img * np.float32(scale))
+    dev.autorange_texture(scale)
+    for key in ('vmin', 'vmax', 'log', 'density_vmin', 'density_vmax'):
+        a, b = host[key], dev[key]
+        if a is None or isinstance(a, (bool, np.bool_)):
+            assert a == b, key
+        else:
+            assert b == pytest.approx(a, rel=2e-5, abs=2e-5), key
+    for key in ('ui_range_linear', 'ui_range_log', 'ui_range_density'):
+        if host[key] is not None:
+            np.testing.assert_allclose(dev[key], host[key], rtol=2e-5, atol=2e-5)

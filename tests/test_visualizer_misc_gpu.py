@@ -26,12 +26,19 @@ def test_split_buffers_give_the_same_image(monkeypatch):
     got = many._sph.get_image()
     big = want[..., 0] > 1e-6 * want[..., 0].max()
     npt.assert_allclose(got[..., 0][big], want[..., 0][big], rtol=1e-4)
-    # a progressive (cell-mapped, multi-range) block also crosses buffer boundaries correctly
-    many._sph._render_progression._recommended_num_particles_to_render = 700
-    many.render_sph(DrawReason.CHANGE)
-    while many._sph.needs_refine():
-        many.render_sph(DrawReason.REFINE)
-    npt.assert_allclose(many._sph.get_image()[..., 0][big], want[..., 0][big], rtol=1e-4)
+    # progressive (cell-mapped, multi-range) frames cross buffer boundaries correctly.  NB with cell mapping the reference
+    # drops cells outside a sphere of 1.2 x scale (sph.py:313), so the fair comparison is progressive vs progressive.
+    def progressive(vis):
+        vis._sph._render_progression._recommended_num_particles_to_render = 700
+        vis.render_sph(DrawReason.CHANGE)
+        while vis._sph.needs_refine():
+            vis.render_sph(DrawReason.REFINE)
+        return vis._sph.get_image()
+
+    p_many = progressive(many)
+    p_one = progressive(one)
+    npt.assert_allclose(p_many[..., 0][big], p_one[..., 0][big], rtol=1e-4)
+    assert many._sph._engine.stats()["particles_submitted"] <= 5000
 
 
 def test_canvas_interaction():

@@ -34,6 +34,15 @@ class Stats(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ContentStats(ctypes.Structure):
+    _fields_ = [("lin_min", ctypes.c_float), ("lin_max", ctypes.c_float), ("log_min", ctypes.c_float),
+                ("log_max", ctypes.c_float), ("n_finite_lin", ctypes.c_int64), ("n_finite_log", ctypes.c_int64),
+                ("any_negative", ctypes.c_int32)]
+
+
+CONTENT_CH0, CONTENT_RATIO, CONTENT_ALL = 0, 1, 2
+
+
 class TsplatError(RuntimeError):
     pass
 
@@ -61,6 +70,8 @@ _SIGNATURES = {
     "tsplat_reduce_colormap": (_i32, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i32, _i32, ctypes.POINTER(ColormapParams), _vp,
                                       _i32, _i32, _vp, _i32, _vp, _vp]),
     "tsplat_periodic_accumulate": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "tsplat_content_stats": (_i32, [_vp, _vp, _i32, _i32, _i32, _f, ctypes.POINTER(ContentStats), _vp]),
+    "tsplat_content_select": (_i32, [_vp, _vp, _i32, _i32, _i32, _f, _i32, _vp, _i32, _vp, _vp]),
     "tsplat_image_axpy": (_i32, [_vp, _vp, _vp, _f, _i64, _vp]),
     "tsplat_cell_layout_work_bytes": (_i64, [_i64, _i32]),
     "tsplat_cell_layout": (_i32, [_i32, _vp, _i64, _i32, ctypes.c_double, ctypes.c_double, _i32, _vp, _vp, _vp, _vp,

@@ -93,6 +93,12 @@ class ColormapHolder:
     sph_raw_output_to_content = _forward("sph_raw_output_to_content")
     del _forward
 
+    def autorange_texture(self, mass_scale: float = 1.0):
+        """Same decisions as ``autorange(image)`` taken on the device from the bound SPH texture (unscaled accumulators
+        times ``mass_scale``), without reading the image back."""
+        self._require_real_colormap()
+        self._impl.autorange_device(self._input_texture.tensor, mass_scale)
+
     def autorange(self, sph_render_output: np.ndarray):
         """Re-derive vmin / vmax (and log vs linear) from an SPH image."""
         self._require_real_colormap()

@@ -173,6 +173,35 @@ class Colormap(ColormapBase):
         self.update_parameters(new_params)
         logger.info(f"Autoscale: log_scale={self._params['log']}, vmin={self._params['vmin']}, vmax={self._params['vmax']}")
 
+    # -- the same decisions taken on the device (no read-back of the image) ------------------------------------------
+    def _content_kind(self):
+        return N.CONTENT_RATIO if self._params.get('weighted_average', False) else N.CONTENT_CH0
+
+    def autorange_device(self, image: torch.Tensor, mass_scale: float):
+        """``autorange_vmin_vmax(image.cpu() * mass_scale)`` without the read-back: statistics and exact order statistics
+        come from the K8 kernels (tsplat_content_stats / tsplat_content_select)."""
+        self._autorange_device_values(image, self._content_kind(), mass_scale)
+
+    def _autorange_device_values(self, image, content, mass_scale):
+        eng = self._device.engine(image.shape[0])
+        st = eng.content_stats(image, content, mass_scale)
+        lin_lo, lin_hi, log_lo, log_hi = st.lin_min, st.lin_max, st.log_min, st.log_max
+        if log_hi == log_lo:
+            log_hi += 1.0; log_lo -= 1.0
+        if lin_hi == lin_lo:
+            lin_hi += 1.0; lin_lo -= 1.0
+        use_log = not bool(st.any_negative)
+        n = st.n_finite_log if use_log else st.n_finite_lin
+        if n > 200:
+            vmin, vmax = eng.content_percentiles(image, content, mass_scale, use_log, n, self.percentile_scaling)
+        elif n > 2:
+            vmin, vmax = (st.log_min, st.log_max) if use_log else (st.lin_min, st.lin_max)
+        else:
+            logger.warning("Problem setting vmin/vmax, perhaps there are no particles or something is wrong with them?")
+            vmin, vmax = 0.0, 1.0
+        self._params['vmin'], self._params['vmax'] = vmin, vmax
+        self.update_parameters({'ui_range_linear': (lin_lo, lin_hi), 'ui_range_log': (log_lo, log_hi), 'log': use_log})
+
     def _update_parameter_buffer(self, width, height, mass_scale):
         """The device image is *unscaled* (sum over the particles rendered so far), so the ranges are shifted instead
         (implementation.py:427-453).  A weighted mean is a ratio and needs no correction."""
@@ -261,6 +290,18 @@ class RGBColormap(Colormap):
     def sph_raw_output_to_content(self, numpy_image: np.ndarray):
         return numpy_image[..., :3]
 
+    def autorange_device(self, image: torch.Tensor, mass_scale: float):
+        eng = self._device.engine(image.shape[0])
+        st = eng.content_stats(image, N.CONTENT_ALL, mass_scale)
+        n = st.n_finite_log
+        if n > 200:
+            self._params['vmax'] = eng.content_percentiles(image, N.CONTENT_ALL, mass_scale, True, n, [self.max_percentile])[0]
+        elif n > 2:
+            self._params['vmax'] = st.log_max
+        else:
+            self._params['vmax'] = 1.0
+        self._params['vmin'] = self._params['vmax'] - self.dynamic_range
+
 
 class RGBHDRColormap(RGBColormap):
     max_percentile = 99.0
@@ -286,6 +327,15 @@ class BivariateColormap(Colormap):
 
     def _generate_mapping_rgba_f32(self, num_points):
         return luts.colormap_table_2d(self._params['colormap_name'], num_points)
+
+    def autorange_device(self, image: torch.Tensor, mass_scale: float):
+        eng = self._device.engine(image.shape[0])
+        st = eng.content_stats(image, N.CONTENT_CH0, mass_scale)
+        density_vmin, density_vmax = eng.content_percentiles(image, N.CONTENT_CH0, mass_scale, True, st.n_finite_log,
+                                                             self.percentile_scaling)
+        self.update_parameters({'density_vmin': density_vmin, 'density_vmax': density_vmax,
+                                'ui_range_density': (st.log_min, st.log_max)})
+        self._autorange_device_values(image, self._content_kind(), mass_scale)
 
     def sph_raw_output_to_content(self, numpy_image: np.ndarray):
         out = numpy_image.copy()

@@ -89,6 +89,7 @@ struct tsplat_ctx {
     void *scratch;
     int64_t scratch_bytes;
     Counters *d_counters;
+    void *d_select;              // histograms / statistics of the device autorange (32 KB)
     // range staging
     int64_t *h_ranges[RANGE_SLOTS];
     int64_t *d_ranges[RANGE_SLOTS];
@@ -1105,6 +1106,109 @@ __global__ void __launch_bounds__(256) k_periodic_accumulate(const PeriodicArgs 
     else reinterpret_cast<float4 *>(a.dst)[pix] = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K8: device-side autorange.  Replaces the host np.percentile of
+// Colormap._autorange_using_values / RGBColormap.autorange_vmin_vmax / BivariateColormap.autorange_vmin_vmax
+// (colormap/implementation.py:381-425, :512-531, :576-588): min/max/sign statistics in one pass, then exact order
+// statistics by a 3-pass (11 + 11 + 10 bit) radix select over the monotone integer image of the float values.
+// ------------------------------------------------------------------------------------------------------------
+enum { CONTENT_CH0 = 0, CONTENT_RATIO = 1, CONTENT_ALL = 2 };
+
+struct ContentArgs {
+    const float *image;
+    int64_t n_values;            // res*res (CH0, RATIO) or res*res*channels (ALL)
+    int channels, content;
+    float scale;
+    int use_log;
+};
+
+__device__ __forceinline__ float content_value(const ContentArgs &a, int64_t i)
+{
+    if (a.content == CONTENT_ALL) return a.image[i] * a.scale;
+    const float c0 = a.image[i * a.channels] * a.scale;
+    if (a.content == CONTENT_CH0) return c0;
+    return (a.image[i * a.channels + 1] * a.scale) / c0;
+}
+
+// order-preserving map float -> uint32 (finite values only)
+__device__ __forceinline__ unsigned float_key(float v)
+{
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__host__ __device__ inline float key_to_float(unsigned k)
+{
+    const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+struct ContentStats {           // device + host layout
+    unsigned lin_min_key, lin_max_key, log_min_key, log_max_key;
+    unsigned any_negative, pad;
+    unsigned long long n_finite_lin, n_finite_log;
+};
+
+__global__ void __launch_bounds__(256) k_content_stats(const ContentArgs a, ContentStats *out)
+{
+    unsigned lmin = 0xffffffffu, lmax = 0u, gmin = 0xffffffffu, gmax = 0u, neg = 0u;
+    unsigned long long nl = 0, ng = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_values; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = content_value(a, i);
+        if (v < 0.0f) neg = 1u;
+        if (isfinite(v)) { const unsigned k = float_key(v); lmin = min(lmin, k); lmax = max(lmax, k); ++nl; }
+        const float lv = log10f(v);
+        if (isfinite(lv)) { const unsigned k = float_key(lv); gmin = min(gmin, k); gmax = max(gmax, k); ++ng; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        lmin = min(lmin, __shfl_down_sync(0xffffffffu, lmin, d)); lmax = max(lmax, __shfl_down_sync(0xffffffffu, lmax, d));
+        gmin = min(gmin, __shfl_down_sync(0xffffffffu, gmin, d)); gmax = max(gmax, __shfl_down_sync(0xffffffffu, gmax, d));
+        neg |= __shfl_down_sync(0xffffffffu, neg, d);
+        nl += __shfl_down_sync(0xffffffffu, nl, d); ng += __shfl_down_sync(0xffffffffu, ng, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out->lin_min_key, lmin); atomicMax(&out->lin_max_key, lmax);
+        atomicMin(&out->log_min_key, gmin); atomicMax(&out->log_max_key, gmax);
+        if (neg) atomicOr(&out->any_negative, 1u);
+        if (nl) atomicAdd(&out->n_finite_lin, nl);
+        if (ng) atomicAdd(&out->n_finite_log, ng);
+    }
+}
+
+constexpr int SELECT_MAX_RANKS = 4;
+struct SelectArgs {
+    ContentArgs c;
+    int n_ranks, shift, bits;              // digit = (key >> shift) & ((1 << bits) - 1)
+    unsigned prefix[SELECT_MAX_RANKS];     // already-resolved high bits of each rank's key
+    unsigned prefix_mask;                  // mask of the resolved bits
+    unsigned *hist;                        // [n_ranks][2048]
+};
+
+__global__ void __launch_bounds__(256) k_content_select(const SelectArgs a)
+{
+    __shared__ unsigned s_hist[SELECT_MAX_RANKS][2048];
+    for (int i = threadIdx.x; i < a.n_ranks * 2048; i += blockDim.x) (&s_hist[0][0])[i] = 0u;
+    __syncthreads();
+    const unsigned dmask = (1u << a.bits) - 1u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.c.n_values; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = content_value(a.c, i);
+        if (a.c.use_log) v = log10f(v);
+        if (!isfinite(v)) continue;
+        const unsigned k = float_key(v);
+        for (int r = 0; r < a.n_ranks; ++r)
+            if ((k & a.prefix_mask) == a.prefix[r]) atomicAdd(&s_hist[r][(k >> a.shift) & dmask], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.n_ranks * 2048; i += blockDim.x) {
+        const unsigned v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&a.hist[i], v);
+    }
+}
+
 __global__ void k_axpy(float *__restrict__ dst, const float *__restrict__ src, float scale, int64_t n)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -1132,6 +1236,7 @@ extern "C" int tsplat_create(int device_ordinal, int resolution, tsplat_ctx **ou
     CUDA_TRY(cudaMalloc(&c->d_lut, LUT_TOTAL * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(Counters)));
     CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(Counters)));
+    CUDA_TRY(cudaMalloc(&c->d_select, sizeof(unsigned) * 4 * 2048));
     for (int s = 0; s < RANGE_SLOTS; ++s) {
         CUDA_TRY(cudaMallocHost(&c->h_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
         CUDA_TRY(cudaMalloc(&c->d_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
@@ -1148,6 +1253,7 @@ extern "C" int tsplat_destroy(tsplat_ctx *c)
     cudaDeviceSynchronize();
     cudaFree(c->d_lut);
     cudaFree(c->d_counters);
+    cudaFree(c->d_select);
     for (int s = 0; s < RANGE_SLOTS; ++s) {
         cudaFreeHost(c->h_ranges[s]);
         cudaFree(c->d_ranges[s]);
@@ -1531,6 +1637,90 @@ extern "C" int tsplat_periodic_accumulate(tsplat_ctx *c, const float *src, float
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+static int content_args(tsplat_ctx *c, const float *image, int res, int channels, int content, float scale, ContentArgs *a)
+{
+    if (!c || !image) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (channels != 1 && channels != 2 && channels != 4) return set_err(TSPLAT_ERR_INVALID, "channels must be 1, 2 or 4");
+    if (res <= 0) return set_err(TSPLAT_ERR_INVALID, "bad resolution");
+    if (content < CONTENT_CH0 || content > CONTENT_ALL) return set_err(TSPLAT_ERR_INVALID, "bad content kind");
+    if (content == CONTENT_RATIO && channels < 2) return set_err(TSPLAT_ERR_INVALID, "ratio needs two channels");
+    a->image = image; a->channels = channels; a->content = content; a->scale = scale; a->use_log = 0;
+    a->n_values = (int64_t)res * res * (content == CONTENT_ALL ? channels : 1);
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_content_stats(tsplat_ctx *c, const float *image, int res, int channels, int content, float scale,
+                                    tsplat_content_stats_t *out, void *stream)
+{
+    if (!out) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    ContentArgs a;
+    int rc = content_args(c, image, res, channels, content, scale, &a);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ContentStats init;
+    memset(&init, 0, sizeof(init));
+    init.lin_min_key = init.log_min_key = 0xffffffffu;
+    ContentStats *d = reinterpret_cast<ContentStats *>(c->d_select);
+    CUDA_TRY(cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_content_stats<<<c->sm_count * 8, 256, 0, st>>>(a, d);
+    c->launches++;
+    ContentStats h;
+    CUDA_TRY(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const float nanf_ = nanf("");
+    out->n_finite_lin = (int64_t)h.n_finite_lin; out->n_finite_log = (int64_t)h.n_finite_log;
+    out->any_negative = (int32_t)h.any_negative;
+    out->lin_min = h.n_finite_lin ? key_to_float(h.lin_min_key) : nanf_;
+    out->lin_max = h.n_finite_lin ? key_to_float(h.lin_max_key) : nanf_;
+    out->log_min = h.n_finite_log ? key_to_float(h.log_min_key) : nanf_;
+    out->log_max = h.n_finite_log ? key_to_float(h.log_max_key) : nanf_;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_content_select(tsplat_ctx *c, const float *image, int res, int channels, int content, float scale,
+                                     int use_log, const int64_t *ranks, int n_ranks, float *out_values, void *stream)
+{
+    if (!ranks || !out_values) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (n_ranks < 1 || n_ranks > SELECT_MAX_RANKS) return set_err(TSPLAT_ERR_INVALID, "n_ranks must be in [1, %d]", SELECT_MAX_RANKS);
+    SelectArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = content_args(c, image, res, channels, content, scale, &a.c);
+    if (rc) return rc;
+    a.c.use_log = use_log ? 1 : 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    a.n_ranks = n_ranks;
+    a.hist = reinterpret_cast<unsigned *>(c->d_select);
+    int64_t remaining[SELECT_MAX_RANKS];
+    for (int r = 0; r < n_ranks; ++r) { if (ranks[r] < 0) return set_err(TSPLAT_ERR_INVALID, "negative rank"); remaining[r] = ranks[r]; }
+    static unsigned h_hist[SELECT_MAX_RANKS * 2048];
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        a.shift = shifts[pass]; a.bits = bits[pass];
+        CUDA_TRY(cudaMemsetAsync(a.hist, 0, sizeof(unsigned) * SELECT_MAX_RANKS * 2048, st));
+        k_content_select<<<c->sm_count * 4, 256, 0, st>>>(a);
+        c->launches++;
+        CUDA_TRY(cudaMemcpyAsync(h_hist, a.hist, sizeof(unsigned) * n_ranks * 2048, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int r = 0; r < n_ranks; ++r) {
+            const unsigned *hh = h_hist + r * 2048;
+            int64_t acc = 0;
+            int bin = -1;
+            for (int b = 0; b < (1 << bits[pass]); ++b) {
+                if (remaining[r] < acc + (int64_t)hh[b]) { bin = b; break; }
+                acc += hh[b];
+            }
+            if (bin < 0) return set_err(TSPLAT_ERR_INVALID, "rank %lld beyond the number of finite values", (long long)ranks[r]);
+            remaining[r] -= acc;
+            a.prefix[r] |= (unsigned)bin << shifts[pass];
+        }
+        a.prefix_mask |= ((1u << bits[pass]) - 1u) << shifts[pass];
+    }
+    for (int r = 0; r < n_ranks; ++r) out_values[r] = key_to_float(a.prefix[r]);
     return TSPLAT_OK;
 }
 

@@ -151,6 +151,34 @@ class SplatEngine:
                                          _ptr(out), out.shape[1], out.shape[0], out_fmt, _stream(self.device)))
         return out
 
+    # -- device-side autorange ------------------------------------------------------------------------------------
+    def content_stats(self, image: torch.Tensor, content: int, scale: float) -> N.ContentStats:
+        st = N.ContentStats()
+        N.check(self.lib.tsplat_content_stats(self._ctx, _ptr(image), image.shape[0], image.shape[2], content,
+                                              ctypes.c_float(scale), ctypes.byref(st), _stream(self.device)))
+        return st
+
+    def content_percentiles(self, image: torch.Tensor, content: int, scale: float, use_log: bool, n_finite: int,
+                            percentiles) -> list:
+        """np.percentile(values[finite], percentiles) (linear interpolation) without leaving the device: exact order
+        statistics from the radix-select kernel, interpolated here."""
+        ranks, fracs = [], []
+        for p in percentiles:
+            pos = p / 100.0 * (n_finite - 1)
+            lo = int(np.floor(pos))
+            ranks += [lo, min(lo + 1, n_finite - 1)]
+            fracs.append(pos - lo)
+        out = []
+        for k in range(0, len(ranks), 4):                       # the kernel resolves up to 4 ranks per sweep
+            chunk = np.ascontiguousarray(ranks[k:k + 4], dtype=np.int64)
+            vals = np.zeros(len(chunk), dtype=np.float32)
+            N.check(self.lib.tsplat_content_select(self._ctx, _ptr(image), image.shape[0], image.shape[2], content,
+                                                   ctypes.c_float(scale), int(bool(use_log)),
+                                                   chunk.ctypes.data_as(ctypes.c_void_p), len(chunk),
+                                                   vals.ctypes.data_as(ctypes.c_void_p), _stream(self.device)))
+            out += list(vals)
+        return [float(out[2 * i]) + (float(out[2 * i + 1]) - float(out[2 * i])) * fracs[i] for i in range(len(percentiles))]
+
     def axpy(self, dst: torch.Tensor, src: torch.Tensor, scale: float):
         N.check(self.lib.tsplat_image_axpy(self._ctx, _ptr(dst), _ptr(src), ctypes.c_float(scale), dst.numel(),
                                            _stream(self.device)))

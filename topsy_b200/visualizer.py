@@ -136,7 +136,7 @@ class VisualizerBase:
         show_colorbar = params['type'] not in ('rgb', 'surface')
         if changed_type or params['vmin'] is None or params['vmax'] is None:
             logger.info("Autorange colormap parameters")
-            self._colormap.autorange(self._sph.get_image())
+            self._autorange()
             params = self._colormap.get_parameters()
         if show_colorbar:
             self._colorbar = ColorbarInfo(params['vmin'], params['vmax'], params['colormap_name'], self._get_colorbar_label())
@@ -256,8 +256,18 @@ class VisualizerBase:
         self._colormap.update_parameters({'vmin': None, 'vmax': None, 'log': None})
         self._initialize_colormap_and_bar()
 
+    use_device_autorange = True      # False: read the image back and use numpy percentiles, like the reference
+
+    def _autorange(self):
+        if self.use_device_autorange:
+            if not self._sph.has_rendered:
+                self._sph.render(DrawReason.EXPORT)
+            self._colormap.autorange_texture(self._sph.last_render_mass_scale)
+        else:
+            self._colormap.autorange(self._sph.get_image())
+
     def colormap_autorange(self):
-        self._colormap.autorange(self._sph.get_image())
+        self._autorange()
         self.invalidate(DrawReason.PRESENTATION_CHANGE)
 
     # -- drawing ----------------------------------------------------------------------------------------------
