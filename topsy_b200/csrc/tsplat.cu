@@ -48,7 +48,7 @@ static int set_err(int code, const char *fmt, ...)
 // ------------------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------------------
-constexpr int TILE = 16;                    // tile edge of the gather path (pixels)
+constexpr int TILE_W = 64, TILE_H = 32;     // tile of the gather path (pixels): 8 warps x (16 x 16) pixel blocks
 constexpr int MAX_RANGES = 1 << 16;         // ranges per render call (reference: <= n_cells = 4096 per buffer)
 constexpr int RANGE_SLOTS = 4;              // pinned staging ring for range tables
 constexpr float DIRECT_MAX_WPX = 8.0f;      // footprints up to this width are splatted by the projecting thread
@@ -99,6 +99,7 @@ struct tsplat_ctx {
     int64_t launches;
     int sm_count;
     bool bin_attr_set;
+    bool gather_attr_set[4];
 };
 
 extern "C" const char *tsplat_last_error(void) { return g_err; }
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(256) k_queue_atomic(const QueueArgs a)
 // ------------------------------------------------------------------------------------------------------------
 // K2: tile binning of the deferred queue (counting sort by 16x16-pixel tile, all on the device)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SEG = 512;                      // pairs per gather work unit
+constexpr int SEG = 1024;                     // pairs per gather work unit
 constexpr unsigned ROUTE_TILED = 1, ROUTE_HUGE = 2;
 
 struct BinArgs {
@@ -525,7 +526,7 @@ __device__ __forceinline__ void tile_range(const Deferred &d, int R, int &tx0, i
     pixel_range(d.px0, d.px1, R, j0, j1);
     pixel_range(d.py0, d.py1, R, k0, k1);
     if (j1 < j0 || k1 < k0) { tx0 = ty0 = 1; tx1 = ty1 = 0; return; }
-    tx0 = j0 / TILE; tx1 = j1 / TILE; ty0 = k0 / TILE; ty1 = k1 / TILE;
+    tx0 = j0 / TILE_W; tx1 = j1 / TILE_W; ty0 = k0 / TILE_H; ty1 = k1 / TILE_H;
 }
 
 constexpr unsigned SMALL_QUEUE = 131072;      // below this many deferred records the binning machinery is not worth it
@@ -718,8 +719,21 @@ __global__ void __launch_bounds__(1024) k_bin_fill(const BinArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K3: tile gather -- one thread per pixel of a 16x16 tile, registers accumulate, no atomics inside the loop
+// K3: tile gather -- pixel-column strips in registers, no atomics inside the loop
 // ------------------------------------------------------------------------------------------------------------
+// A tile is TILE_W x TILE_H = 64 x 32 pixels; persistent 256-thread CTAs pull (tile, <= SEG-pair segment) tickets.
+// Each warp owns a 16 x 16 block of the tile and each lane ONE pixel column of 8 rows in it (column = lane & 15,
+// rows (lane >> 4) * 8 .. + 7), with the 8 x C partial sums in registers.
+//
+// Nearest-texel sampling (every footprint below 64 px) is separable in the index: K[k][j] = T[iv(k)][iu(j)].
+//   * iv(k) is the same for every pixel of an image row, so the CTA computes it ONCE per (record, tile row) while
+//     staging a batch, as a ready-made LUT row offset (16 bits; rows outside the footprint point at a row of zeros);
+//   * iu(j) is computed by the lane once per record for its column (columns outside the footprint select a zero
+//     column: every LUT level is stored with one extra, zero, column);
+//   * a pixel update is then  LDS lut[row_off[k] + iu]  +  one FFMA per channel: no per-pixel coverage tests, no
+//     per-pixel float->int conversions.  Shared-memory bandwidth (one 4-byte gather per pixel) is the bound.
+// Bilinear records (footprint >= 64 px) take a warp-uniform slow branch with the full sampler.
+// Per-warp lists (built with shared-memory atomics while staging) keep warps off records that miss their block.
 struct GatherArgs {
     const Deferred *queue;
     const unsigned int *pairs;
@@ -732,141 +746,201 @@ struct GatherArgs {
     int R, ntx, nt;
 };
 
-// Per-record sampling constants hoisted out of the pixel loop.  Bit-identical to sample_lut():
-//   nearest:  floor(((fx - px0) * inv) * n) == floor((fx - px0) * (inv * n))   because n is a power of two,
-//             and the lower clamp is dropped because a covered pixel has fx >= px0 (and fy < py1), so u, v >= 0.
-struct GatherRec {
-    float4 a;       // px0 px1 py0 py1
-    float4 b;       // scale (= inv * n, or inv when bilinear), v0, v1, v2
-    int n;          // texels per side, 0 => bilinear on level 0
-    int base;       // float offset of the level inside the LUT
+// shared-memory copy of the kernel LUT: level l (n = 64 >> l) is n rows of n + 1 floats (last column zero), followed
+// by 65 zeros that invalid rows point at.  Odd row strides also spread a LUT column over all banks.
+constexpr int PLUT_ZERO = 5560;               // 64*65 + 32*33 + 16*17 + 8*9
+constexpr int PLUT_TOTAL = 5632;              // 5560 + 65, rounded up
+__host__ __device__ constexpr int plut_offset(int level) { return level == 0 ? 0 : level == 1 ? 4160 : level == 2 ? 5216 : 5488; }
+constexpr int G_BATCH = 256;                  // records staged per round (one per thread)
+constexpr int LEVEL_BILINEAR = 4;
+constexpr int GATHER_CTAS_PER_SM = 4;        // sizeof(GatherSmem) = 53 KB
+
+struct GatherSmem {
+    float lut[PLUT_TOTAL];
+    float4 a[G_BATCH];                        // px0 px1 scale v0      (scale = inv * n, or inv when bilinear)
+    float4 y[G_BATCH];                        // py0 py1 scale level
+    float2 v[G_BATCH];                        // v1 v2
+    unsigned short row[G_BATCH][TILE_H];      // LUT row offset of every tile row
+    unsigned short list[8][G_BATCH];          // per-warp record lists: record | level << 8
+    unsigned nlist[8];
+    unsigned work[4];                         // tile, first pair, pair count
 };
 
-__device__ __forceinline__ float sample_rec(const float *__restrict__ lut, float scale, int n, int base,
-                                            float px0, float py1, float fx, float fy)
+// bilinear sample of the padded level 0 (row stride 65); bit-identical to sample_lut()'s magnification branch
+__device__ __forceinline__ float sample_bilinear_padded(const float *__restrict__ lut, float inv, float px0, float py1,
+                                                        float fx, float fy)
 {
-    if (n == 0) {           // magnification: bilinear on the 64 x 64 level
-        const float u = (fx - px0) * scale, v = (py1 - fy) * scale;
-        const float tu = fmaf(u, 64.0f, -0.5f), tv = fmaf(v, 64.0f, -0.5f);
-        const float iu = floorf(tu), iv = floorf(tv);
-        const float fu = tu - iu, fv = tv - iv;
-        const int a = (int)iu, b = (int)iv;
-        const int a0 = min(max(a, 0), 63), a1 = min(max(a + 1, 0), 63);
-        const int b0 = min(max(b, 0), 63), b1 = min(max(b + 1, 0), 63);
-        const float t00 = lut[b0 * 64 + a0], t01 = lut[b0 * 64 + a1];
-        const float t10 = lut[b1 * 64 + a0], t11 = lut[b1 * 64 + a1];
-        const float top = fmaf(fu, t01 - t00, t00);
-        const float bot = fmaf(fu, t11 - t10, t10);
-        return fmaf(fv, bot - top, top);
-    }
-    const int iu = min(__float2int_rd((fx - px0) * scale), n - 1);
-    const int iv = min(__float2int_rd((py1 - fy) * scale), n - 1);
-    return lut[base + iv * n + iu];
+    const float u = (fx - px0) * inv, v = (py1 - fy) * inv;
+    const float tu = fmaf(u, 64.0f, -0.5f), tv = fmaf(v, 64.0f, -0.5f);
+    const float iu = floorf(tu), iv = floorf(tv);
+    const float fu = tu - iu, fv = tv - iv;
+    const int a = (int)iu, b = (int)iv;
+    const int a0 = min(max(a, 0), 63), a1 = min(max(a + 1, 0), 63);
+    const int b0 = min(max(b, 0), 63), b1 = min(max(b + 1, 0), 63);
+    const float t00 = lut[b0 * 65 + a0], t01 = lut[b0 * 65 + a1];
+    const float t10 = lut[b1 * 65 + a0], t11 = lut[b1 * 65 + a1];
+    const float top = fmaf(fu, t01 - t00, t00);
+    const float bot = fmaf(fu, t11 - t10, t10);
+    return fmaf(fv, bot - top, top);
+}
+
+template <int MODE>
+__device__ __forceinline__ void gather_accumulate(float (&acc)[8][ModeTraits<MODE>::C], int k, float K, float v0, float v1,
+                                                  float v2, float cnt)
+{
+    constexpr int C = ModeTraits<MODE>::C;
+    acc[k][0] = fmaf(K, v0, acc[k][0]);
+    if (C >= 2) acc[k][1 % C] = fmaf(K, v1, acc[k][1 % C]);          // WEIGHTED / DEPTH: v1 = v0 * (q | cz)
+    if (C == 4) { acc[k][2 % C] = fmaf(K, v2, acc[k][2 % C]); acc[k][3 % C] += cnt; }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
 {
     constexpr int C = ModeTraits<MODE>::C;
-    constexpr int BATCH = 256;
-    __shared__ float s_lut[LUT_TOTAL];
-    __shared__ float4 s_a[BATCH];                 // px0 px1 py0 py1
-    __shared__ float4 s_b[BATCH];                 // scale v0 v1 v2
-    __shared__ int2 s_c[BATCH];                   // n, base
-    __shared__ unsigned char s_list[8][BATCH];    // per-warp list of the batch records that touch the warp's block
-    __shared__ unsigned s_nlist[8];
-    __shared__ unsigned s_work[3];                // tile, first pair, pair count
+    extern __shared__ __align__(16) unsigned char g_smem_raw[];
+    GatherSmem &S = *reinterpret_cast<GatherSmem *>(g_smem_raw);
     const unsigned n_seg = a.counters->n_segments;
     if (n_seg == 0u) return;
-    for (int i = threadIdx.x; i < LUT_TOTAL; i += blockDim.x) s_lut[i] = a.lut[i];
-    // each warp owns an 8 x 4 pixel block of the tile (2 x 4 blocks per tile)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = (warp & 1) * 8, by = (warp >> 1) * 4;
-    const int lx = bx + (lane & 7), ly = by + (lane >> 3);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < PLUT_TOTAL; i += 256) S.lut[i] = 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int level = 0; level < 4; ++level) {
+        const int n = 64 >> level, sh = 6 - level;
+        for (int i = tid; i < n * n; i += 256)
+            S.lut[plut_offset(level) + (i >> sh) * (n + 1) + (i & (n - 1))] = a.lut[lut_offset(level) + i];
+    }
+    const int lx = (warp & 3) * 16 + (lane & 15);         // pixel column inside the tile
+    const int ly0 = (warp >> 2) * 16 + (lane >> 4) * 8;   // first of the lane's 8 rows inside the tile
 
     for (;;) {
-        __syncthreads();                                  // s_work / batch buffers free (and LUT loaded on round 0)
-        if (threadIdx.x == 0) {
+        __syncthreads();                                  // work / batch buffers free (and LUT loaded on round 0)
+        if (tid == 0) {
             const unsigned ticket = atomicAdd(&a.counters->work_counter, 1u);
             if (ticket < n_seg) {
                 const unsigned l = a.seg_tile[ticket];
                 const unsigned first = a.tile_offset[l] + (ticket - a.seg_prefix[l]) * SEG;
                 const unsigned end = a.tile_offset[l + 1];
-                s_work[0] = l; s_work[1] = first; s_work[2] = min((unsigned)SEG, end - first);
+                S.work[0] = l; S.work[1] = first; S.work[2] = min((unsigned)SEG, end - first);
             } else {
-                s_work[0] = 0xffffffffu;
+                S.work[0] = 0xffffffffu;
             }
         }
-        if (threadIdx.x < 8) s_nlist[threadIdx.x] = 0u;
+        if (tid < 8) S.nlist[tid] = 0u;
         __syncthreads();
-        const unsigned tile = s_work[0];
+        const unsigned tile = S.work[0];
         if (tile == 0xffffffffu) break;
-        const unsigned first = s_work[1], count = s_work[2];
+        const unsigned first = S.work[1], count = S.work[2];
         const int tx = (int)(tile % (unsigned)a.ntx), ty = (int)(tile / (unsigned)a.ntx);
-        const int px = tx * TILE + lx, py = ty * TILE + ly;
-        const float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
-        const float tcx = (float)(tx * TILE) + 0.5f, tcy = (float)(ty * TILE) + 0.5f;   // first pixel centre of the tile
-        float acc[C];
+        const int px = tx * TILE_W + lx, py0 = ty * TILE_H + ly0;
+        const float fx = (float)px + 0.5f;
+        const float tcx = (float)(tx * TILE_W) + 0.5f, tcy = (float)(ty * TILE_H) + 0.5f;   // first pixel centre of the tile
+        float acc[8][C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[k][c] = 0.0f;
 
-        for (unsigned b0 = 0; b0 < count; b0 += BATCH) {
-            const unsigned nb = min((unsigned)BATCH, count - b0);
+        for (unsigned b0 = 0; b0 < count; b0 += G_BATCH) {
+            const unsigned nb = min((unsigned)G_BATCH, count - b0);
             if (b0) {
                 __syncthreads();
-                if (threadIdx.x < 8) s_nlist[threadIdx.x] = 0u;
+                if (tid < 8) S.nlist[tid] = 0u;
                 __syncthreads();
             }
-            if (threadIdx.x < nb) {
-                const unsigned ridx = a.pairs[first + b0 + threadIdx.x];
-                const float4 q0 = reinterpret_cast<const float4 *>(a.queue + ridx)[0];
-                const float4 q1 = reinterpret_cast<const float4 *>(a.queue + ridx)[1];
+            // ---- stage: one record per thread -------------------------------------------------------------
+            if ((unsigned)tid < nb) {
+                const unsigned ridx = a.pairs[first + b0 + tid];
+                const float4 q0 = reinterpret_cast<const float4 *>(a.queue + ridx)[0];      // px0 px1 py0 py1
+                const float4 q1 = reinterpret_cast<const float4 *>(a.queue + ridx)[1];      // wpx v0 v1 v2
                 const float wpx = q1.x, inv = 1.0f / wpx;
-                int n, base; float scale;
-                if (wpx >= 64.0f) { n = 0; base = 0; scale = inv; }
+                int level; float scale;
+                if (wpx >= 64.0f) { level = LEVEL_BILINEAR; scale = inv; }
                 else {
-                    const int level = wpx > LEVEL_T0 ? 0 : wpx > LEVEL_T1 ? 1 : wpx > LEVEL_T2 ? 2 : 3;
-                    n = 64 >> level; base = lut_offset(level); scale = inv * (float)n;
+                    level = wpx > LEVEL_T0 ? 0 : wpx > LEVEL_T1 ? 1 : wpx > LEVEL_T2 ? 2 : 3;
+                    scale = inv * (float)(64 >> level);
                 }
-                s_a[threadIdx.x] = q0;
-                s_b[threadIdx.x] = make_float4(scale, q1.y, q1.z, q1.w);
-                s_c[threadIdx.x] = make_int2(n, base);
-                // which of the 8 warp blocks (8 x 4 pixel centres each) does the record's span touch?
+                S.a[tid] = make_float4(q0.x, q0.y, scale, q1.y);
+                S.y[tid] = make_float4(q0.z, q0.w, scale, __int_as_float(level));
+                if (C == 2) S.v[tid] = make_float2(q1.y * q1.z, 0.0f);       // (m/h^2) * (q | cz)
+                if (C == 4) S.v[tid] = make_float2(q1.z, q1.w);
+                const unsigned short entry = (unsigned short)(tid | (level << 8));
+                // which of the 8 warp blocks (16 x 16 pixel centres each) does the record's span touch?
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
-                    const float x0 = tcx + (float)((w & 1) * 8), y0 = tcy + (float)((w >> 1) * 4);
-                    if (x0 < q0.y && x0 + 7.0f >= q0.x && y0 < q0.w && y0 + 3.0f >= q0.z)
-                        s_list[w][atomicAdd(&s_nlist[w], 1u)] = (unsigned char)threadIdx.x;
+                    const float x0 = tcx + (float)((w & 3) * 16), y0 = tcy + (float)((w >> 2) * 16);
+                    if (x0 < q0.y && x0 + 15.0f >= q0.x && y0 < q0.w && y0 + 15.0f >= q0.z)
+                        S.list[w][atomicAdd(&S.nlist[w], 1u)] = entry;
                 }
             }
             __syncthreads();
-            const unsigned nl = s_nlist[warp];
+            // ---- stage: LUT row offset of every (record, tile row); lane = tile row -------------------------
+            {
+                const float fy = tcy + (float)lane;
+                for (unsigned r = warp; r < nb; r += 8) {
+                    const float4 Y = S.y[r];
+                    const int level = __float_as_int(Y.w);
+                    if (level < LEVEL_BILINEAR) {
+                        const int n = 64 >> level;
+                        const bool ok = fy >= Y.x && fy < Y.y;
+                        const int iv = min(__float2int_rd((Y.y - fy) * Y.z), n - 1);
+                        S.row[r][lane] = (unsigned short)(ok ? plut_offset(level) + iv * (n + 1) : PLUT_ZERO);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- accumulate: every warp walks its own list ------------------------------------------------
+            const unsigned nl = S.nlist[warp];
             for (unsigned i = 0; i < nl; ++i) {
-                const unsigned r = s_list[warp][i];
-                const float4 A = s_a[r];
-                if (fx >= A.x && fx < A.y && fy >= A.z && fy < A.w) {
-                    const float4 B = s_b[r];
-                    const int2 Cc = s_c[r];
-                    const float K = sample_rec(s_lut, B.x, Cc.x, Cc.y, A.x, A.w, fx, fy);
-                    if (MODE == TSPLAT_MODE_RGB) {
-                        acc[0] += B.y * K; acc[1 % C] += B.z * K; acc[2 % C] += B.w * K; acc[3 % C] += 1.0f;
-                    } else {
-                        const float val = K * B.y;
-                        acc[0] += val;
-                        if (C == 2) acc[1 % C] += val * B.z;
+                const unsigned e = S.list[warp][i];
+                const unsigned r = e & 0xffu;
+                const int level = (int)(e >> 8);
+                const float4 A = S.a[r];
+                const bool colok = fx >= A.x && fx < A.y;
+                float v1 = 0.0f, v2 = 0.0f;
+                if (C >= 2) { const float2 V = S.v[r]; v1 = V.x; v2 = V.y; }
+                if (level < LEVEL_BILINEAR) {
+                    const int n = 64 >> level;
+                    int iu = min(__float2int_rd((fx - A.x) * A.z), n - 1);
+                    iu = colok ? iu : n;
+                    const uint4 rw = *reinterpret_cast<const uint4 *>(&S.row[r][ly0]);
+                    const unsigned w4[4] = {rw.x, rw.y, rw.z, rw.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const unsigned r0 = w4[q] & 0xffffu, r1 = w4[q] >> 16;
+                        const float K0 = S.lut[r0 + iu], K1 = S.lut[r1 + iu];
+                        gather_accumulate<MODE>(acc, 2 * q, K0, A.w, v1, v2, (colok && r0 != PLUT_ZERO) ? 1.0f : 0.0f);
+                        gather_accumulate<MODE>(acc, 2 * q + 1, K1, A.w, v1, v2, (colok && r1 != PLUT_ZERO) ? 1.0f : 0.0f);
+                    }
+                } else {
+                    const float4 Y = S.y[r];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float fy = (float)(py0 + k) + 0.5f;
+                        if (colok && fy >= Y.x && fy < Y.y) {
+                            const float K = sample_bilinear_padded(S.lut, A.z, A.x, Y.y, fx, fy);
+                            gather_accumulate<MODE>(acc, k, K, A.w, v1, v2, 1.0f);
+                        }
                     }
                 }
             }
         }
-        if (px < a.R && py < a.R) {
-            const size_t pix = (size_t)py * a.R + px;
-            if (C == 1) { if (acc[0] != 0.0f) atomicAdd(a.image + pix, acc[0]); }
-            else if (C == 2) {
-                if (acc[0] != 0.0f || acc[1 % C] != 0.0f)
-                    atomicAdd(reinterpret_cast<float2 *>(a.image) + pix, make_float2(acc[0], acc[1 % C]));
-            } else {
-                if (acc[3 % C] != 0.0f)
-                    atomicAdd(reinterpret_cast<float4 *>(a.image) + pix, make_float4(acc[0], acc[1 % C], acc[2 % C], acc[3 % C]));
+        if (px < a.R) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int py = py0 + k;
+                if (py >= a.R) break;
+                const size_t pix = (size_t)py * a.R + px;
+                if (C == 1) { if (acc[k][0] != 0.0f) atomicAdd(a.image + pix, acc[k][0]); }
+                else if (C == 2) {
+                    if (acc[k][0] != 0.0f || acc[k][1 % C] != 0.0f)
+                        atomicAdd(reinterpret_cast<float2 *>(a.image) + pix, make_float2(acc[k][0], acc[k][1 % C]));
+                } else {
+                    if (acc[k][3 % C] != 0.0f)
+                        atomicAdd(reinterpret_cast<float4 *>(a.image) + pix,
+                                  make_float4(acc[k][0], acc[k][1 % C], acc[k][2 % C], acc[k][3 % C]));
+                }
             }
         }
     }
@@ -1333,8 +1407,8 @@ static ScratchLayout scratch_layout(int R, int64_t cap)
     L.queue_cap = cap;
     L.pairs_cap = cap * PAIRS_PER_PARTICLE;
     if (L.pairs_cap > 0xfffffff0ll) L.pairs_cap = 0xfffffff0ll;
-    L.ntx = (R + TILE - 1) / TILE;
-    L.nt = L.ntx * L.ntx;
+    L.ntx = (R + TILE_W - 1) / TILE_W;
+    L.nt = L.ntx * ((R + TILE_H - 1) / TILE_H);
     int64_t o = 0;
     L.queue_off = o;   o += align_up(cap * (int64_t)sizeof(Deferred), 256);
     L.route_off = o;   o += align_up(cap, 256);
@@ -1429,7 +1503,11 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
         ga.queue = pa.queue; ga.pairs = ba.pairs; ga.tile_offset = ba.tile_offset; ga.seg_prefix = ba.seg_prefix;
         ga.seg_tile = ba.seg_tile;
         ga.counters = c->d_counters; ga.lut = c->d_lut; ga.image = c->image; ga.R = c->R; ga.ntx = L.ntx; ga.nt = L.nt;
-        k_tile_gather<MODE><<<c->sm_count * 6, 256, 0, st>>>(ga);
+        if (!c->gather_attr_set[MODE]) {
+            CUDA_TRY(cudaFuncSetAttribute(k_tile_gather<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GatherSmem)));
+            c->gather_attr_set[MODE] = true;
+        }
+        k_tile_gather<MODE><<<c->sm_count * GATHER_CTAS_PER_SM, 256, sizeof(GatherSmem), st>>>(ga);
         QueueArgs qa;
         qa.queue = pa.queue; qa.indices = ba.huge_idx; qa.count = &c->d_counters->huge_count; qa.cap = pa.queue_cap;
         qa.lut = c->d_lut; qa.image = c->image; qa.R = c->R;
