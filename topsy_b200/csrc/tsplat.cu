@@ -727,11 +727,14 @@ __global__ void __launch_bounds__(1024) k_bin_fill(const BinArgs a)
 //
 // Nearest-texel sampling (every footprint below 64 px) is separable in the index: K[k][j] = T[iv(k)][iu(j)].
 //   * iv(k) is the same for every pixel of an image row, so the CTA computes it ONCE per (record, tile row) while
-//     staging a batch, as a ready-made LUT row offset (16 bits; rows outside the footprint point at a row of zeros);
+//     staging a batch, as a ready-made 16-bit shared-memory address of the LUT row (rows outside the footprint point
+//     at a row of zeros);
 //   * iu(j) is computed by the lane once per record for its column (columns outside the footprint select a zero
-//     column: every LUT level is stored with one extra, zero, column);
-//   * a pixel update is then  LDS lut[row_off[k] + iu]  +  one FFMA per channel: no per-pixel coverage tests, no
-//     per-pixel float->int conversions.  Shared-memory bandwidth (one 4-byte gather per pixel) is the bound.
+//     column: every LUT level is stored with one extra zero row and column);
+//   * a pixel update is then  ld.shared [row_addr[k] + col_term]  +  one FFMA per channel: no per-pixel coverage
+//     tests, no per-pixel float->int conversions; two row addresses are advanced by one packed 2 x 16-bit add.
+// Levels 1..3 are stored twice, interleaved (texel = 8 bytes): the lower half-warp reads the even words, the upper
+// half-warp (8 rows further down) the odd ones, so the two halves can never collide on a bank.
 // Bilinear records (footprint >= 64 px) take a warp-uniform slow branch with the full sampler.
 // Per-warp lists (built with shared-memory atomics while staging) keep warps off records that miss their block.
 struct GatherArgs {
@@ -746,25 +749,25 @@ struct GatherArgs {
     int R, ntx, nt;
 };
 
-// shared-memory copy of the kernel LUT: level l (n = 64 >> l) is n rows of n + 1 floats (last column zero), followed
-// by 65 zeros that invalid rows point at.  Odd row strides also spread a LUT column over all banks.
-constexpr int PLUT_ZERO = 5560;               // 64*65 + 32*33 + 16*17 + 8*9
-constexpr int PLUT_TOTAL = 5632;              // 5560 + 65, rounded up
-__host__ __device__ constexpr int plut_offset(int level) { return level == 0 ? 0 : level == 1 ? 4160 : level == 2 ? 5216 : 5488; }
+// shared-memory copy of the kernel LUT (float offsets): level 0 = 65 x 65 floats (row 64 / column 64 zero);
+// level l >= 1 (n = 64 >> l) = (n + 1) x (n + 1) texels of 2 identical floats (row n / column n zero).
+constexpr int PLUT_FLOATS = 7144;             // 4226 + 2*33*33 + 2*17*17 + 2*9*9
+__host__ __device__ constexpr int plut_base(int level) { return level == 0 ? 0 : level == 1 ? 4226 : level == 2 ? 6404 : 6982; }
+__host__ __device__ constexpr int plut_row_bytes(int level) { return level == 0 ? 260 : 8 * ((64 >> level) + 1); }
 constexpr int G_BATCH = 256;                  // records staged per round (one per thread)
-constexpr int LEVEL_BILINEAR = 4;
-constexpr int GATHER_CTAS_PER_SM = 4;        // sizeof(GatherSmem) = 53 KB
+constexpr int GATHER_CTAS_PER_SM = 3;         // sizeof(GatherSmem) = 62 KB
 
 struct GatherSmem {
-    float lut[PLUT_TOTAL];
+    float lut[PLUT_FLOATS];
     float4 a[G_BATCH];                        // px0 px1 scale v0      (scale = inv * n, or inv when bilinear)
-    float4 y[G_BATCH];                        // py0 py1 scale level
+    float4 y[G_BATCH];                        // py0 py1 scale packed(level-base address | n << 16 | row bytes << 23)
     float2 v[G_BATCH];                        // v1 v2
-    unsigned short row[G_BATCH][TILE_H];      // LUT row offset of every tile row
-    unsigned short list[8][G_BATCH];          // per-warp record lists: record | level << 8
-    unsigned nlist[8];
+    unsigned short row[G_BATCH][TILE_H];      // shared-memory address of the LUT row of every tile row
+    unsigned list[8][G_BATCH];                // per-warp record lists: record * 16 | n << 16   (n == 0: bilinear)
+    unsigned nlist[16];                       // [0..7] nearest-texel entries (from the front), [8..15] bilinear (from the back)
     unsigned work[4];                         // tile, first pair, pair count
 };
+static_assert(sizeof(GatherSmem) * GATHER_CTAS_PER_SM <= 227 * 1024, "gather shared memory");
 
 // bilinear sample of the padded level 0 (row stride 65); bit-identical to sample_lut()'s magnification branch
 __device__ __forceinline__ float sample_bilinear_padded(const float *__restrict__ lut, float inv, float px0, float py1,
@@ -782,6 +785,18 @@ __device__ __forceinline__ float sample_bilinear_padded(const float *__restrict_
     const float top = fmaf(fu, t01 - t00, t00);
     const float bot = fmaf(fu, t11 - t10, t10);
     return fmaf(fv, bot - top, top);
+}
+
+// Eight LUT gathers of one lane, predicated on `p` (the lane's column is inside the footprint).  Lanes that are off do
+// not take part in the access, so they cannot cause bank conflicts; their K registers keep an earlier (finite) LUT
+// value that the caller multiplies by zero.  The LUT is read-only after the first barrier (no memory clobber needed).
+__device__ __forceinline__ void lds8_pred(float (&K)[8], const unsigned (&ad)[8], bool p)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %16, 0;\n\t"
+        "@p ld.shared.f32 %0, [%8];\n\t@p ld.shared.f32 %1, [%9];\n\t@p ld.shared.f32 %2, [%10];\n\t@p ld.shared.f32 %3, [%11];\n\t"
+        "@p ld.shared.f32 %4, [%12];\n\t@p ld.shared.f32 %5, [%13];\n\t@p ld.shared.f32 %6, [%14];\n\t@p ld.shared.f32 %7, [%15];\n\t}"
+        : "+f"(K[0]), "+f"(K[1]), "+f"(K[2]), "+f"(K[3]), "+f"(K[4]), "+f"(K[5]), "+f"(K[6]), "+f"(K[7])
+        : "r"(ad[0]), "r"(ad[1]), "r"(ad[2]), "r"(ad[3]), "r"(ad[4]), "r"(ad[5]), "r"(ad[6]), "r"(ad[7]), "r"((unsigned)p));
 }
 
 template <int MODE>
@@ -803,16 +818,24 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
     const unsigned n_seg = a.counters->n_segments;
     if (n_seg == 0u) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < PLUT_TOTAL; i += 256) S.lut[i] = 0.0f;
+    for (int i = tid; i < PLUT_FLOATS; i += 256) S.lut[i] = 0.0f;
     __syncthreads();
+    for (int i = tid; i < 64 * 64; i += 256) S.lut[(i >> 6) * 65 + (i & 63)] = a.lut[i];
 #pragma unroll
-    for (int level = 0; level < 4; ++level) {
+    for (int level = 1; level < 4; ++level) {
         const int n = 64 >> level, sh = 6 - level;
-        for (int i = tid; i < n * n; i += 256)
-            S.lut[plut_offset(level) + (i >> sh) * (n + 1) + (i & (n - 1))] = a.lut[lut_offset(level) + i];
+        for (int i = tid; i < n * n; i += 256) {
+            const float t = a.lut[lut_offset(level) + i];
+            reinterpret_cast<float2 *>(S.lut + plut_base(level))[(i >> sh) * (n + 1) + (i & (n - 1))] = make_float2(t, t);
+        }
     }
+    const unsigned lut_sa = (unsigned)__cvta_generic_to_shared(S.lut);      // < 64 KB: row addresses fit 16 bits
     const int lx = (warp & 3) * 16 + (lane & 15);         // pixel column inside the tile
     const int ly0 = (warp >> 2) * 16 + (lane >> 4) * 8;   // first of the lane's 8 rows inside the tile
+    const unsigned half4 = (unsigned)(lane >> 4) * 4u;    // which copy of an interleaved texel this half-warp reads
+    const unsigned *my_list = S.list[warp];
+    float Kreg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // LUT values of the current record (see lds8_pred)
+    float Kreg2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};    // ... and of the second record in flight
 
     for (;;) {
         __syncthreads();                                  // work / batch buffers free (and LUT loaded on round 0)
@@ -827,7 +850,7 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                 S.work[0] = 0xffffffffu;
             }
         }
-        if (tid < 8) S.nlist[tid] = 0u;
+        if (tid < 16) S.nlist[tid] = 0u;
         __syncthreads();
         const unsigned tile = S.work[0];
         if (tile == 0xffffffffu) break;
@@ -846,7 +869,7 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
             const unsigned nb = min((unsigned)G_BATCH, count - b0);
             if (b0) {
                 __syncthreads();
-                if (tid < 8) S.nlist[tid] = 0u;
+                if (tid < 16) S.nlist[tid] = 0u;
                 __syncthreads();
             }
             // ---- stage: one record per thread -------------------------------------------------------------
@@ -855,73 +878,102 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                 const float4 q0 = reinterpret_cast<const float4 *>(a.queue + ridx)[0];      // px0 px1 py0 py1
                 const float4 q1 = reinterpret_cast<const float4 *>(a.queue + ridx)[1];      // wpx v0 v1 v2
                 const float wpx = q1.x, inv = 1.0f / wpx;
-                int level; float scale;
-                if (wpx >= 64.0f) { level = LEVEL_BILINEAR; scale = inv; }
+                unsigned n, packed; float scale;
+                if (wpx >= 64.0f) { n = 0u; packed = 0u; scale = inv; }
                 else {
-                    level = wpx > LEVEL_T0 ? 0 : wpx > LEVEL_T1 ? 1 : wpx > LEVEL_T2 ? 2 : 3;
-                    scale = inv * (float)(64 >> level);
+                    const int level = wpx > LEVEL_T0 ? 0 : wpx > LEVEL_T1 ? 1 : wpx > LEVEL_T2 ? 2 : 3;
+                    n = 64u >> level;
+                    scale = inv * (float)n;
+                    packed = (lut_sa + 4u * (unsigned)plut_base(level)) | (n << 16) | ((unsigned)plut_row_bytes(level) << 23);
                 }
                 S.a[tid] = make_float4(q0.x, q0.y, scale, q1.y);
-                S.y[tid] = make_float4(q0.z, q0.w, scale, __int_as_float(level));
+                S.y[tid] = make_float4(q0.z, q0.w, scale, __uint_as_float(packed));
                 if (C == 2) S.v[tid] = make_float2(q1.y * q1.z, 0.0f);       // (m/h^2) * (q | cz)
                 if (C == 4) S.v[tid] = make_float2(q1.z, q1.w);
-                const unsigned short entry = (unsigned short)(tid | (level << 8));
+                const unsigned entry = ((unsigned)tid << 4) | (n << 16);
                 // which of the 8 warp blocks (16 x 16 pixel centres each) does the record's span touch?
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
                     const float x0 = tcx + (float)((w & 3) * 16), y0 = tcy + (float)((w >> 2) * 16);
-                    if (x0 < q0.y && x0 + 15.0f >= q0.x && y0 < q0.w && y0 + 15.0f >= q0.z)
-                        S.list[w][atomicAdd(&S.nlist[w], 1u)] = entry;
+                    if (x0 < q0.y && x0 + 15.0f >= q0.x && y0 < q0.w && y0 + 15.0f >= q0.z) {
+                        if (n) S.list[w][atomicAdd(&S.nlist[w], 1u)] = entry;
+                        else S.list[w][G_BATCH - 1 - atomicAdd(&S.nlist[8 + w], 1u)] = entry;
+                    }
                 }
             }
             __syncthreads();
-            // ---- stage: LUT row offset of every (record, tile row); lane = tile row -------------------------
+            // ---- stage: LUT row address of every (record, tile row); lane = tile row ------------------------
             {
                 const float fy = tcy + (float)lane;
                 for (unsigned r = warp; r < nb; r += 8) {
                     const float4 Y = S.y[r];
-                    const int level = __float_as_int(Y.w);
-                    if (level < LEVEL_BILINEAR) {
-                        const int n = 64 >> level;
+                    const unsigned packed = __float_as_uint(Y.w);
+                    const int n = (int)((packed >> 16) & 127u);
+                    if (n) {
                         const bool ok = fy >= Y.x && fy < Y.y;
                         const int iv = min(__float2int_rd((Y.y - fy) * Y.z), n - 1);
-                        S.row[r][lane] = (unsigned short)(ok ? plut_offset(level) + iv * (n + 1) : PLUT_ZERO);
+                        S.row[r][lane] = (unsigned short)((packed & 0xffffu) + (unsigned)(ok ? iv : n) * (packed >> 23));
                     }
                 }
             }
             __syncthreads();
-            // ---- accumulate: every warp walks its own list ------------------------------------------------
-            const unsigned nl = S.nlist[warp];
-            for (unsigned i = 0; i < nl; ++i) {
-                const unsigned e = S.list[warp][i];
-                const unsigned r = e & 0xffu;
-                const int level = (int)(e >> 8);
-                const float4 A = S.a[r];
+            // ---- accumulate: every warp walks its own lists ------------------------------------------------
+            // nearest-texel records (front of the list): branch-free body, two records in flight to cover LDS latency
+            auto nearest = [&](const unsigned e, float (&K)[8]) {
+                const unsigned r16 = e & 0xfff0u;
+                const int n = (int)(e >> 16);
+                const float4 A = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.a) + r16);
+                const uint4 rw = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(S.row) + r16 * 4u + ly0 * 2);
                 const bool colok = fx >= A.x && fx < A.y;
                 float v1 = 0.0f, v2 = 0.0f;
-                if (C >= 2) { const float2 V = S.v[r]; v1 = V.x; v2 = V.y; }
-                if (level < LEVEL_BILINEAR) {
-                    const int n = 64 >> level;
-                    int iu = min(__float2int_rd((fx - A.x) * A.z), n - 1);
-                    iu = colok ? iu : n;
-                    const uint4 rw = *reinterpret_cast<const uint4 *>(&S.row[r][ly0]);
-                    const unsigned w4[4] = {rw.x, rw.y, rw.z, rw.w};
+                if (C >= 2) { const float2 V = *reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(S.v) + (r16 >> 1)); v1 = V.x; v2 = V.y; }
+                const int iu = min(__float2int_rd((fx - A.x) * A.z), n - 1);      // garbage (unused) where !colok
+                const unsigned col = n == 64 ? (unsigned)iu * 4u : (unsigned)iu * 8u + half4;
+                const unsigned col2 = col * 0x10001u;                 // the same column term for both packed rows
+                const unsigned w4[4] = {rw.x, rw.y, rw.z, rw.w};
+                unsigned ad[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const unsigned r0 = w4[q] & 0xffffu, r1 = w4[q] >> 16;
-                        const float K0 = S.lut[r0 + iu], K1 = S.lut[r1 + iu];
-                        gather_accumulate<MODE>(acc, 2 * q, K0, A.w, v1, v2, (colok && r0 != PLUT_ZERO) ? 1.0f : 0.0f);
-                        gather_accumulate<MODE>(acc, 2 * q + 1, K1, A.w, v1, v2, (colok && r1 != PLUT_ZERO) ? 1.0f : 0.0f);
-                    }
-                } else {
-                    const float4 Y = S.y[r];
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned X = w4[q] + col2;                  // no carry: both halves stay below 64 K
+                    ad[2 * q] = X & 0xffffu; ad[2 * q + 1] = X >> 16;
+                }
+                lds8_pred(K, ad, colok);
+                const float m0 = colok ? A.w : 0.0f, m1 = colok ? v1 : 0.0f, m2 = colok ? v2 : 0.0f;
+                float2 Yr = make_float2(0.f, 0.f);
+                if (C == 4) { const float4 Y = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.y) + r16); Yr = make_float2(Y.x, Y.y); }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 8; ++k) {
+                    float cnt = 0.0f;
+                    if (C == 4) {                                     // RGB counts every covered pixel, even where K == 0
                         const float fy = (float)(py0 + k) + 0.5f;
-                        if (colok && fy >= Y.x && fy < Y.y) {
-                            const float K = sample_bilinear_padded(S.lut, A.z, A.x, Y.y, fx, fy);
-                            gather_accumulate<MODE>(acc, k, K, A.w, v1, v2, 1.0f);
-                        }
+                        cnt = (colok && fy >= Yr.x && fy < Yr.y) ? 1.0f : 0.0f;
+                    }
+                    gather_accumulate<MODE>(acc, k, K[k], m0, m1, m2, cnt);
+                }
+            };
+            const unsigned nl = S.nlist[warp];
+            unsigned i = 0;
+            for (; i + 2 <= nl; i += 2) {
+                const uint2 ee = *reinterpret_cast<const uint2 *>(my_list + i);
+                nearest(ee.x, Kreg);
+                nearest(ee.y, Kreg2);
+            }
+            if (i < nl) nearest(my_list[i], Kreg);
+            // bilinear records (back of the list; footprints of 64 px and more are rare): full sampler
+            const unsigned nlb = S.nlist[8 + warp];
+            for (unsigned ib = 0; ib < nlb; ++ib) {
+                const unsigned r16 = my_list[G_BATCH - 1 - ib] & 0xfff0u;
+                const float4 A = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.a) + r16);
+                const float4 Y = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.y) + r16);
+                const bool colok = fx >= A.x && fx < A.y;
+                float v1 = 0.0f, v2 = 0.0f;
+                if (C >= 2) { const float2 V = *reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(S.v) + (r16 >> 1)); v1 = V.x; v2 = V.y; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float fy = (float)(py0 + k) + 0.5f;
+                    if (colok && fy >= Y.x && fy < Y.y) {
+                        const float K = sample_bilinear_padded(S.lut, A.z, A.x, Y.y, fx, fy);
+                        gather_accumulate<MODE>(acc, k, K, A.w, v1, v2, 1.0f);
                     }
                 }
             }
