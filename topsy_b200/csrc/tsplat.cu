@@ -302,37 +302,53 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     unsigned cells4 = 0;                          // cell counts of the lane's 4 particles, 8 bits each (<= 64)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        if (e < e_first || e >= e_last) continue;
-        const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
-        if (!p.keep) { ++n_culled; continue; }
-        int j0, j1, k0, k1;
-        pixel_range(p.px0, p.px1, a.R, j0, j1);
-        pixel_range(p.py0, p.py1, a.R, k0, k1);
-        if (j1 < j0 || k1 < k0) { ++n_direct; continue; }     // no pixel centre covered (sub-pixel or off-screen)
-        const float rhh = 1.0f / (hs[e] * hs[e]);
-        const float v0 = w0s[e] * rhh;
-        float v1, v2 = 0.0f;
-        if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] * rhh; v2 = w2s[e] * rhh; }
-        else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
-        else v1 = w1s[e];
-        if (p.wpx <= DIRECT_MAX_WPX && j1 - j0 < K1_MAX_SPAN && k1 - k0 < K1_MAX_SPAN) {
-            ++n_direct;
-            const int cj0 = j0 >> CELL_SHIFT;
-            const unsigned ncj = (unsigned)((j1 >> CELL_SHIFT) - cj0 + 1);
-            cells4 |= (ncj * (unsigned)(k1 - k0 + 1)) << (8 * e);
-            DirectRec &r = s_rec[warp][e * 32 + lane];      // slot e*32+lane: conflict-free 128-bit stores
-            *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.py1, 1.0f / p.wpx, v0);
-            *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)),
-                                                              __uint_as_float((unsigned)j0 | ((unsigned)j1 << 16)));
-            r.ncj = ncj;
-            r.magic = c_magic[ncj];
-        } else {
-            ++n_deferred;
-            const unsigned slot = atomicAdd(&a.counters->q_count, 1u);
-            if (slot < a.queue_cap) {
+        bool defer = false;
+        float4 dq0 = make_float4(0.f, 0.f, 0.f, 0.f), dq1 = dq0;
+        if (e >= e_first && e < e_last) {
+            const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
+            int j0, j1, k0, k1;
+            pixel_range(p.px0, p.px1, a.R, j0, j1);
+            pixel_range(p.py0, p.py1, a.R, k0, k1);
+            if (!p.keep) ++n_culled;
+            else if (j1 < j0 || k1 < k0) ++n_direct;          // no pixel centre covered (sub-pixel or off-screen)
+            else {
+                const float rhh = 1.0f / (hs[e] * hs[e]);
+                const float v0 = w0s[e] * rhh;
+                float v1, v2 = 0.0f;
+                if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] * rhh; v2 = w2s[e] * rhh; }
+                else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
+                else v1 = w1s[e];
+                if (p.wpx <= DIRECT_MAX_WPX && j1 - j0 < K1_MAX_SPAN && k1 - k0 < K1_MAX_SPAN) {
+                    ++n_direct;
+                    const int cj0 = j0 >> CELL_SHIFT;
+                    const unsigned ncj = (unsigned)((j1 >> CELL_SHIFT) - cj0 + 1);
+                    cells4 |= (ncj * (unsigned)(k1 - k0 + 1)) << (8 * e);
+                    DirectRec &r = s_rec[warp][e * 32 + lane];      // slot e*32+lane: conflict-free 128-bit stores
+                    *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.py1, 1.0f / p.wpx, v0);
+                    *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)),
+                                                                      __uint_as_float((unsigned)j0 | ((unsigned)j1 << 16)));
+                    r.ncj = ncj;
+                    r.magic = c_magic[ncj];
+                } else {
+                    ++n_deferred;
+                    defer = true;
+                    dq0 = make_float4(p.px0, p.px1, p.py0, p.py1);
+                    dq1 = make_float4(p.wpx, v0, v1, v2);
+                }
+            }
+        }
+        // warp-aggregated queue append: one global atomic per warp and e (a same-address ATOMG per particle serialises
+        // in the L2 once most particles are deferred)
+        const unsigned dm = __ballot_sync(0xffffffffu, defer);
+        if (dm) {
+            unsigned qb = 0;
+            if (lane == 0) qb = atomicAdd(&a.counters->q_count, (unsigned)__popc(dm));
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            const unsigned slot = qb + __popc(dm & lt_mask);
+            if (defer && slot < a.queue_cap) {
                 float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
-                q[0] = make_float4(p.px0, p.px1, p.py0, p.py1);
-                q[1] = make_float4(p.wpx, v0, v1, v2);
+                q[0] = dq0;
+                q[1] = dq1;
             }
         }
     }
