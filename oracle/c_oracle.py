@@ -38,6 +38,9 @@ def lib():
         _lib.oracle_count_updates.restype = ctypes.c_int
         _lib.oracle_count_updates.argtypes = [fp, fp, fp, fp, ctypes.c_int64, fp, ctypes.c_float, ctypes.c_int, ip, ip]
         _lib.oracle_num_threads.restype = ctypes.c_int
+        _lib.oracle_splat_surface.restype = ctypes.c_int
+        _lib.oracle_splat_surface.argtypes = [fp, fp, fp, fp, fp, fp, ctypes.c_int64, ip, ip, ctypes.c_int, fp, ctypes.c_float,
+                                              fp, ctypes.c_int, ctypes.c_float, fp, fp, ctypes.c_int, ctypes.c_int]
     return _lib
 
 
@@ -70,6 +73,28 @@ def splat(x, y, z, h, weights, M, sf, R, mode, lut, ranges=None, out=None, clear
             int(R), int(mode), _ptr(img, acc_t), int(bool(clear)), int(nthreads))
     if rc != 0:
         raise RuntimeError(f"oracle splat failed rc={rc}")
+    return img
+
+
+def splat_surface(x, y, z, h, m, q, M, sf, R, lut, density_cut, ranges=None, out=None, zbuf=None, clear=True,
+                  clamp_depth=False):
+    """Z-buffered surface splat (see oracle_splat_surface): (R, R, 2) float32 = (quantity, depth)."""
+    L = lib()
+    x, y, z, h, m, q = (_f32(a) for a in (x, y, z, h, m, q))
+    img = np.zeros((R, R, 2), np.float32) if out is None else out
+    if clamp_depth and zbuf is None:
+        zbuf = np.zeros((R, R), np.float32)
+    M = _f32(np.asarray(M).reshape(16)); lut = _f32(lut)
+    if ranges is None:
+        st = ln = None; nr = 0
+    else:
+        st = np.ascontiguousarray(ranges[0], np.int64); ln = np.ascontiguousarray(ranges[1], np.int64); nr = len(st)
+    rc = L.oracle_splat_surface(_ptr(x), _ptr(y), _ptr(z), _ptr(h), _ptr(m), _ptr(q), len(x), _ptr(st, ctypes.c_int64),
+                                _ptr(ln, ctypes.c_int64), nr, _ptr(M), ctypes.c_float(float(sf)), _ptr(lut), int(R),
+                                ctypes.c_float(float(density_cut)), _ptr(img), _ptr(zbuf), int(bool(clear)),
+                                int(bool(clamp_depth)))
+    if rc != 0:
+        raise RuntimeError(f"oracle surface splat failed rc={rc}")
     return img
 
 

@@ -174,6 +174,75 @@ int NAME(const float *x, const float *y, const float *z, const float *h,        
 DEFINE_SPLAT(oracle_splat_f64, double)
 DEFINE_SPLAT(oracle_splat_f32, float)
 
+
+/*
+ * Surface render mode: z-buffered splat of the front-most particles above a density cut.
+ *   src/topsy/shaders/sph.wgsl:93-120   vertex_depth_with_cut: rho = m / h^3 > density_cut, intensities = (q, clip z, h*sf*0.5)
+ *   src/topsy/shaders/sph.wgsl:148-158  fragment_raw: K = textureSample(local-sphere kernel); discard if K < 0;
+ *                                       depth = z + (h*sf*0.5)*K; output (q, depth), frag_depth = depth
+ *   src/topsy/sph.py:455-470, :592-599  blend = replace, depth_compare = greater, depth cleared to 0
+ * `lut` is the local-sphere mip chain (sph.py:446-455: sqrt(4 - d^2) inside the sphere, -0.01 outside; no normalisation).
+ * img is (R, R, 2) float32 = (q, depth); 0 where nothing was drawn.
+ *
+ * clamp_depth != 0: the reference's depth test on frag_depth clamped to the viewport range [0, 1] (WebGPU), first
+ *                   drawn fragment wins ties, `zbuf` (R*R floats, caller-provided) holds the depth attachment.
+ * clamp_depth == 0: what the CUDA path does: per pixel the fragment with the largest (unclamped) depth wins, ties go
+ *                   to the larger bit pattern of q -- order independent, so it can be compared bit-for-bit.  The two
+ *                   differ only where a pixel receives more than one fragment deeper than 1.0.
+ * Arithmetic contract: rho = m / ((h*h)*h) with fp32 multiplies (WGSL's pow(h, 3.0) is only accurate to a few ULP and
+ * implementation dependent), depth = z + hz*K with separate multiply and add.
+ */
+int oracle_splat_surface(const float *x, const float *y, const float *z, const float *h, const float *m, const float *q,
+                         int64_t n, const int64_t *starts, const int64_t *lens, int nranges, const float *M, float sf,
+                         const float *lut, int R, float density_cut, float *img, float *zbuf, int clear, int clamp_depth)
+{
+    if (R <= 0 || (clamp_depth && !zbuf)) return -1;
+    int64_t one_start = 0, one_len = n;
+    if (nranges <= 0 || !starts) { starts = &one_start; lens = &one_len; nranges = 1; }
+    for (int r = 0; r < nranges; ++r) if (starts[r] < 0 || starts[r] + lens[r] > n) return -2;
+    if (clear) {
+        memset(img, 0, (size_t)R * R * 2 * sizeof(float));
+        if (zbuf) memset(zbuf, 0, (size_t)R * R * sizeof(float));
+    }
+    const float Rf = (float)R;
+    for (int r = 0; r < nranges; ++r) {
+        for (int64_t i = starts[r]; i < starts[r] + lens[r]; ++i) {
+            const float rho = m[i] / ((h[i] * h[i]) * h[i]);
+            if (!(rho > density_cut)) continue;
+            proj_t p = project(x[i], y[i], z[i], h[i], M, sf, Rf);
+            if (!p.keep) continue;
+            int j0, j1, k0, k1;
+            bounds(p.px0, p.px1, R, &j0, &j1);
+            bounds(p.py0, p.py1, R, &k0, &k1);
+            if (j1 < j0 || k1 < k0) continue;
+            const float hz = (h[i] * sf) * 0.5f;
+            for (int k = k0; k <= k1; ++k) {
+                float fy = (float)k + 0.5f;
+                if (!(fy >= p.py0 && fy < p.py1)) continue;
+                for (int j = j0; j <= j1; ++j) {
+                    float fx = (float)j + 0.5f;
+                    if (!(fx >= p.px0 && fx < p.px1)) continue;
+                    float K = sample_lut(lut, &p, fx, fy);
+                    if (K < 0.0f) continue;
+                    float t = hz * K;
+                    float depth = p.cz + t;
+                    float *px = img + ((size_t)k * R + j) * 2;
+                    if (clamp_depth) {
+                        float d = depth < 0.0f ? 0.0f : (depth > 1.0f ? 1.0f : depth);
+                        if (d > zbuf[(size_t)k * R + j]) { zbuf[(size_t)k * R + j] = d; px[0] = q[i]; px[1] = depth; }
+                    } else {
+                        uint32_t db, qb, odb, oqb;
+                        memcpy(&db, &depth, 4); memcpy(&qb, &q[i], 4); memcpy(&odb, &px[1], 4); memcpy(&oqb, &px[0], 4);
+                        uint64_t key = ((uint64_t)db << 32) | qb, old = ((uint64_t)odb << 32) | oqb;
+                        if (depth > 0.0f && key > old) { px[0] = q[i]; px[1] = depth; }
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 /* Number of (particle, pixel) updates and culled particles: the "work" term of the second roofline. */
 int oracle_count_updates(const float *x, const float *y, const float *z, const float *h, int64_t n,
                          const float *M, float sf, int R, int64_t *n_updates, int64_t *n_culled)

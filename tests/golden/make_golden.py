@@ -68,6 +68,22 @@ def reference_goldens():
     print("reference_goldens.npz:", {k: out[k].shape for k in wanted})
 
 
+def surface_goldens():
+    """Known answers of the surface render mode: tests/test_render_output.py::test_surface_render (:448-556) and
+    tests/test_smooth.py::test_smoothing_operation (bilateral filter, atol 1e-6) -> surface_goldens.npz"""
+    out = {}
+    for rel, fn, names in (("test_render_output.py", "test_surface_render",
+                            ["quantity_expectation", "depth_expectation", "presentation_expectation"]),
+                           ("test_smooth.py", "test_smoothing_operation", ["expected_global_samples", "expected_edge_check"])):
+        tree = ast.parse((REF / "tests" / rel).read_text())
+        node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == fn)
+        found = _literal_arrays(node)
+        for name in names:
+            out[f"{fn}__{name}"] = found[name]
+    np.savez_compressed(OUT / "surface_goldens.npz", **out)
+    print("surface_goldens.npz:", {k: v.shape for k, v in out.items()})
+
+
 def load_reference_modules():
     wgpu = types.ModuleType("wgpu"); wgpu.GPUDevice = object
     pynbody = types.ModuleType("pynbody"); pynbody.snapshot = types.ModuleType("pynbody.snapshot")
@@ -165,5 +181,9 @@ def scheduling_goldens():
 
 
 if __name__ == "__main__":
-    reference_goldens()
-    scheduling_goldens()
+    if len(sys.argv) > 1 and sys.argv[1] == "surface":      # added later; leaves the older fixture files untouched
+        surface_goldens()
+    else:
+        reference_goldens()
+        scheduling_goldens()
+        surface_goldens()
