@@ -39,10 +39,13 @@ typedef enum {
     TSPLAT_MODE_DENSITY = 0,   /* vertex_weighting/fragment_weighting with quantity == 0: 1 channel  K*m/h^2      */
     TSPLAT_MODE_WEIGHTED = 1,  /* vertex_weighting/fragment_weighting (sph.wgsl:75-83,138-146): (K m/h^2, K m/h^2 q) */
     TSPLAT_MODE_RGB = 2,       /* vertex_rgb/fragment_rgb (sph.wgsl:68-73,160-165): (K r/h^2, K g/h^2, K b/h^2, 1)   */
-    TSPLAT_MODE_DEPTH = 3      /* vertex_depth/fragment_weighting (sph.wgsl:85-91): (K m/h^2, K m/h^2 z_clip)        */
+    TSPLAT_MODE_DEPTH = 3,     /* vertex_depth/fragment_weighting (sph.wgsl:85-91): (K m/h^2, K m/h^2 z_clip)        */
+    TSPLAT_MODE_SURFACE = 4    /* vertex_depth_with_cut/fragment_raw (sph.wgsl:93-158) with depth_compare = greater and
+                                  blending off (sph.py:457-601): z-buffered (quantity, depth) of the front-most particle
+                                  above the density cut; w0 = mass, w1 = quantity; needs tsplat_set_surface()          */
 } tsplat_mode;
 
-/* channels accumulated per pixel for a mode: 1, 2, 4, 2 */
+/* channels per pixel for a mode: 1, 2, 4, 2, 2 */
 int tsplat_mode_channels(int mode);
 
 typedef enum {
@@ -141,6 +144,34 @@ int tsplat_reduce_colormap(tsplat_ctx *ctx, const float *const *peer_images, int
  * quad.  offsets_xy / weights are HOST arrays. */
 int tsplat_periodic_accumulate(tsplat_ctx *ctx, const float *src, float *dst, int channels, const float *offsets_xy,
                                const float *weights, int n, void *stream);
+
+/* Surface render mode.  tsplat_set_surface replaces DepthSPHWithOcclusion's kernel texture (the LocalSphereKernel mip
+ * chain, sph.py:446-455,497-501: 5440 host floats, same layout as tsplat_set_kernel_lut) and its density_cut uniform
+ * (sph.py:503-506).  TSPLAT_MODE_SURFACE renders use this LUT instead of the SPH kernel LUT. */
+int tsplat_set_surface(tsplat_ctx *ctx, const float *host_lut, int n_floats, float density_cut);
+
+/* Replaces ColorAsSurfaceMap._encode_smoothing_filter_pass (colormap/surface.py:262-297, shaders/smooth.wgsl): bilateral
+ * filter of channel 1 of a width x height x 2 device image (channel 0 is copied); in != out. */
+int tsplat_bilateral_filter(tsplat_ctx *ctx, const float *in, float *out, int width, int height, float spatial_sigma,
+                            float range_sigma, int kernel_size, void *stream);
+
+/* The uniform block of shaders/surface.wgsl:14-24 (colormap/surface.py:341-354) plus its preprocessor switches. */
+typedef struct {
+    float depth_scale;
+    float light_direction[3];
+    float light_color[3];
+    float ambient_color[3];
+    float vmin, vmax;
+    float window_aspect_ratio;      /* width/height of the output */
+    int32_t material_colormap;      /* MATERIAL_COLORMAP: colour the surface by channel 0 through the 1-D LUT */
+    int32_t log_scale;              /* MATERIAL_LOG */
+} tsplat_surface_params;
+
+/* Replaces ColorAsSurfaceMap's render pass (shaders/surface.wgsl): normals from central differences of the smoothed depth
+ * (channel 1 of the res x res x 2 device image), Lambert + ambient lighting dimmed with depth, optional material colormap
+ * (lut: device float32 RGBA, lut_w texels).  out: device buffer out_w*out_h*4 elements of out_fmt. */
+int tsplat_surface_shade(tsplat_ctx *ctx, const float *smoothed, int res, const tsplat_surface_params *params,
+                         const float *lut, int lut_w, void *out, int out_w, int out_h, int out_fmt, void *stream);
 
 /* Device-side autorange (replaces the host read-back + np.percentile of colormap/implementation.py:381-425,
  * :512-531, :576-588).  "content" selects what the colormap looks at: 0 = channel 0 * scale (density), 1 = channel 1 /

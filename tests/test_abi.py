@@ -35,7 +35,7 @@ def test_pure_host_entry_points():
     from topsy_b200 import _native as N
     lib = N.lib()
     assert lib.tsplat_abi_version() == 1
-    assert [lib.tsplat_mode_channels(m) for m in range(4)] == [1, 2, 4, 2]
+    assert [lib.tsplat_mode_channels(m) for m in range(5)] == [1, 2, 4, 2, 2]
     assert lib.tsplat_mode_channels(9) == -1
     assert lib.tsplat_scratch_bytes(2048, 1 << 20) > (1 << 20) * 32
     assert lib.tsplat_cell_layout_work_bytes(1000, 16) > 0

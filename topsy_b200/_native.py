@@ -9,8 +9,8 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libtsplat.so"
 
-MODE_DENSITY, MODE_WEIGHTED, MODE_RGB, MODE_DEPTH = 0, 1, 2, 3
-MODE_CHANNELS = {MODE_DENSITY: 1, MODE_WEIGHTED: 2, MODE_RGB: 4, MODE_DEPTH: 2}
+MODE_DENSITY, MODE_WEIGHTED, MODE_RGB, MODE_DEPTH, MODE_SURFACE = 0, 1, 2, 3, 4
+MODE_CHANNELS = {MODE_DENSITY: 1, MODE_WEIGHTED: 2, MODE_RGB: 4, MODE_DEPTH: 2, MODE_SURFACE: 2}
 FMT_RGBA8, FMT_RGBA16F, FMT_RGBA32F = 0, 1, 2
 CMAP_DENSITY, CMAP_WEIGHTED, CMAP_BIVARIATE, CMAP_BIVARIATE_WEIGHTED, CMAP_RGB = 0, 1, 2, 3, 4
 LUT_TOTAL = 5440
@@ -23,6 +23,12 @@ class ColormapParams(ctypes.Structure):
                 ("density_vmin", ctypes.c_float), ("density_vmax", ctypes.c_float),
                 ("window_aspect_ratio", ctypes.c_float), ("gamma", ctypes.c_float),
                 ("kind", ctypes.c_int32), ("log_scale", ctypes.c_int32)]
+
+
+class SurfaceParams(ctypes.Structure):
+    _fields_ = [("depth_scale", ctypes.c_float), ("light_direction", ctypes.c_float * 3), ("light_color", ctypes.c_float * 3),
+                ("ambient_color", ctypes.c_float * 3), ("vmin", ctypes.c_float), ("vmax", ctypes.c_float),
+                ("window_aspect_ratio", ctypes.c_float), ("material_colormap", ctypes.c_int32), ("log_scale", ctypes.c_int32)]
 
 
 class Stats(ctypes.Structure):
@@ -69,6 +75,9 @@ _SIGNATURES = {
                                _i32, _vp]),
     "tsplat_reduce_colormap": (_i32, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i32, _i32, ctypes.POINTER(ColormapParams), _vp,
                                       _i32, _i32, _vp, _i32, _vp, _vp]),
+    "tsplat_set_surface": (_i32, [_vp, _vp, _i32, _f]),
+    "tsplat_bilateral_filter": (_i32, [_vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
+    "tsplat_surface_shade": (_i32, [_vp, _vp, _i32, ctypes.POINTER(SurfaceParams), _vp, _i32, _vp, _i32, _i32, _i32, _vp]),
     "tsplat_periodic_accumulate": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "tsplat_content_stats": (_i32, [_vp, _vp, _i32, _i32, _i32, _f, ctypes.POINTER(ContentStats), _vp]),
     "tsplat_content_select": (_i32, [_vp, _vp, _i32, _i32, _i32, _f, _i32, _vp, _i32, _vp, _vp]),

@@ -14,6 +14,7 @@ from .. import config
 from . import implementation, luts  # noqa: F401
 from .implementation import (BivariateColormap, Colormap, ColormapBase, NoColormap, RGBColormap,  # noqa: F401
                              RGBHDRColormap)
+from .surface import ColorAsSurfaceMap  # noqa: F401  (registers the 'surface' implementation)
 
 _UNINITIALISED = {'colormap_name': config.DEFAULT_COLORMAP, 'vmin': None, 'vmax': None, 'log': False, 'type': 'none'}
 

@@ -79,6 +79,9 @@ struct tsplat_ctx {
     int device;
     int R;
     float *d_lut;                // LUT_TOTAL floats
+    float *d_slut;               // local-sphere LUT of the surface mode (LUT_TOTAL floats)
+    float density_cut;
+    bool surface_set;
     bool lut_set, camera_set;
     Camera cam;
     const float *x, *y, *z, *h;
@@ -111,6 +114,7 @@ extern "C" int tsplat_mode_channels(int mode)
     case TSPLAT_MODE_WEIGHTED: return 2;
     case TSPLAT_MODE_RGB: return 4;
     case TSPLAT_MODE_DEPTH: return 2;
+    case TSPLAT_MODE_SURFACE: return 2;
     default: return -1;
     }
 }
@@ -1014,6 +1018,8 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
     }
 }
 
+#include "tsplat_surface.cuh"
+
 // ------------------------------------------------------------------------------------------------------------
 // K5: fused normalise + log/linear + colormap LUT  (colormap.wgsl:75-159)
 // ------------------------------------------------------------------------------------------------------------
@@ -1156,6 +1162,42 @@ __global__ void __launch_bounds__(256) k_colormap(const CmapArgs a)
 
     const float4 rgba = colormap_value(v, a.p, a.lut, a.lut_w, a.lut_h);
     store_rgba(a.out, (size_t)oy * a.out_w + ox, a.out_fmt, rgba);
+}
+
+// K11: surface lighting (surface.wgsl:24-123); the sampling helpers live in tsplat_surface.cuh
+__global__ void __launch_bounds__(256) k_surface_shade(const tsplat_surface::ShadeArgs a)
+{
+    using tsplat_surface::sample_rg;
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y;
+    if (ox >= a.out_w || oy >= a.out_h) return;
+    // vertex_main: the square image covers the larger window dimension (same mapping as colormap.wgsl)
+    const float asp = a.p.window_aspect_ratio;
+    const float sx = asp > 1.0f ? 1.0f : 1.0f / asp, sy = asp > 1.0f ? asp : 1.0f;
+    const float X = -1.0f + (2.0f * ox + 1.0f) / (float)a.out_w;
+    const float Y = 1.0f - (2.0f * oy + 1.0f) / (float)a.out_h;
+    const float u = (X / sx + 1.0f) * 0.5f, v = (1.0f - Y / sy) * 0.5f;
+    const bool linear = (float)a.res / fmaxf((float)a.out_w, (float)a.out_h) <= 1.0f;
+    const float tx = 1.0f / (float)a.out_w, ty = 1.0f / (float)a.out_h;       // uniforms.texelSize
+    const float ds = a.p.depth_scale;
+    const float2 centre = sample_rg(a.image, a.res, u, v, linear);
+    const float d_l = sample_rg(a.image, a.res, u - tx, v, linear).y * ds, d_r = sample_rg(a.image, a.res, u + tx, v, linear).y * ds;
+    const float d_u = sample_rg(a.image, a.res, u, v - ty, linear).y * ds, d_d = sample_rg(a.image, a.res, u, v + ty, linear).y * ds;
+    const float dX = (d_r - d_l) * 0.5f, dY = (d_d - d_u) * 0.5f;
+    const float nlen = sqrtf(dX * dX + dY * dY + tx * tx);
+    const float nx = -dX / nlen, ny = -dY / nlen, nz = tx / nlen;
+    const float ndotl = fmaxf(nx * a.p.light_direction[0] + ny * a.p.light_direction[1] + nz * a.p.light_direction[2], 0.0f);
+    float mat[3] = {1.0f, 1.0f, 1.0f};
+    if (a.p.material_colormap) {
+        float val = centre.x;
+        if (a.p.log_scale) val = wgsl_log10(val);
+        const float4 c = lut_sample_1d(a.lut, a.lut_w, clamp01((val - a.p.vmin) / (a.p.vmax - a.p.vmin)));
+        mat[0] = c.x; mat[1] = c.y; mat[2] = c.z;
+    }
+    const float dim = fminf(fmaxf(centre.y * ds, 0.0f), 0.5f) * 2.0f;
+    float rgb[3];
+    for (int c = 0; c < 3; ++c) rgb[c] = (a.p.light_color[c] * ndotl * mat[c] + a.p.ambient_color[c] * mat[c]) * dim;
+    store_rgba(a.out, (size_t)oy * a.out_w + ox, a.out_fmt, make_float4(rgb[0], rgb[1], rgb[2], 1.0f));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1376,6 +1418,7 @@ extern "C" int tsplat_create(int device_ordinal, int resolution, tsplat_ctx **ou
     CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaMalloc(&c->d_lut, LUT_TOTAL * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->d_slut, LUT_TOTAL * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(Counters)));
     CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(Counters)));
     CUDA_TRY(cudaMalloc(&c->d_select, sizeof(unsigned) * 4 * 2048));
@@ -1394,6 +1437,7 @@ extern "C" int tsplat_destroy(tsplat_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     cudaFree(c->d_lut);
+    cudaFree(c->d_slut);
     cudaFree(c->d_counters);
     cudaFree(c->d_select);
     for (int s = 0; s < RANGE_SLOTS; ++s) {
@@ -1586,19 +1630,40 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
     return TSPLAT_OK;
 }
 
+// surface mode: project + inline z-buffer fragments, then the deferred (large) footprints; no binning needed
+static int launch_render_surface(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups, cudaStream_t st)
+{
+    const int64_t blocks = (n_groups + 255) / 256;
+    if (blocks > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
+    CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, 6 * sizeof(unsigned int), st));
+    if (blocks > 0) {
+        ProjectArgs a2 = pa;
+        a2.lut = c->d_slut;
+        tsplat_surface::k_project_surface<<<(unsigned)blocks, 256, 0, st>>>(a2, c->density_cut);
+        QueueArgs qa;
+        qa.queue = pa.queue; qa.indices = nullptr; qa.count = &c->d_counters->q_count; qa.cap = pa.queue_cap;
+        qa.lut = c->d_slut; qa.image = c->image; qa.R = c->R;
+        tsplat_surface::k_queue_surface<<<c->sm_count * 8, 256, 0, st>>>(qa);
+        c->launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
 extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t *lens, int n_ranges, int mode,
                              int clear, void *stream)
 {
     if (!c) return set_err(TSPLAT_ERR_INVALID, "NULL context");
     const int C = tsplat_mode_channels(mode);
     if (C < 0) return set_err(TSPLAT_ERR_INVALID, "unknown mode %d", mode);
-    if (!c->lut_set) return set_err(TSPLAT_ERR_STATE, "kernel LUT not set");
+    if (mode == TSPLAT_MODE_SURFACE ? !c->surface_set : !c->lut_set)
+        return set_err(TSPLAT_ERR_STATE, mode == TSPLAT_MODE_SURFACE ? "surface LUT / density cut not set" : "kernel LUT not set");
     if (!c->camera_set) return set_err(TSPLAT_ERR_STATE, "camera not set");
     if (!c->image) return set_err(TSPLAT_ERR_STATE, "image not set");
     if (c->channels != C) return set_err(TSPLAT_ERR_INVALID, "mode %d needs a %d-channel image, have %d", mode, C, c->channels);
     if (c->n > 0 && !c->x) return set_err(TSPLAT_ERR_STATE, "particles not set");
     if (c->n > 0 && !c->w0) return set_err(TSPLAT_ERR_STATE, "weights not set");
-    if ((mode == TSPLAT_MODE_WEIGHTED || mode == TSPLAT_MODE_RGB) && c->n > 0 && !c->w1)
+    if ((mode == TSPLAT_MODE_WEIGHTED || mode == TSPLAT_MODE_RGB || mode == TSPLAT_MODE_SURFACE) && c->n > 0 && !c->w1)
         return set_err(TSPLAT_ERR_STATE, "second weight array not set");
     if (mode == TSPLAT_MODE_RGB && c->n > 0 && !c->w2) return set_err(TSPLAT_ERR_STATE, "third weight array not set");
     if (n_ranges < 0 || n_ranges > MAX_RANGES) return set_err(TSPLAT_ERR_INVALID, "n_ranges %d out of [0, %d]", n_ranges, MAX_RANGES);
@@ -1645,6 +1710,7 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
         a2.queue_cap = (unsigned)(chunk_cap < n_particles ? chunk_cap : n_particles);
         a2.n_groups = n_groups;
         switch (mode) {
+        case TSPLAT_MODE_SURFACE: return launch_render_surface(c, a2, n_groups, st);
         case TSPLAT_MODE_DENSITY: return launch_render<TSPLAT_MODE_DENSITY>(c, a2, n_groups, L, st);
         case TSPLAT_MODE_WEIGHTED: return launch_render<TSPLAT_MODE_WEIGHTED>(c, a2, n_groups, L, st);
         case TSPLAT_MODE_RGB: return launch_render<TSPLAT_MODE_RGB>(c, a2, n_groups, L, st);
@@ -1728,6 +1794,59 @@ extern "C" int tsplat_colormap(tsplat_ctx *c, const float *image, int image_res,
     a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_w = out_w; a.out_h = out_h; a.out_fmt = out_fmt;
     dim3 grid((out_w + 255) / 256, out_h);
     k_colormap<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    c->launches++;
+    c->last_stream = (cudaStream_t)stream;
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_set_surface(tsplat_ctx *c, const float *host_lut, int n_floats, float density_cut)
+{
+    if (!c) return set_err(TSPLAT_ERR_INVALID, "NULL context");
+    if (host_lut) {
+        if (n_floats != LUT_TOTAL) return set_err(TSPLAT_ERR_INVALID, "surface LUT must have %d floats, got %d", LUT_TOTAL, n_floats);
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaMemcpy(c->d_slut, host_lut, LUT_TOTAL * sizeof(float), cudaMemcpyHostToDevice));
+        c->surface_set = true;
+    } else if (!c->surface_set) {
+        return set_err(TSPLAT_ERR_STATE, "surface LUT not set yet: pass it with the first call");
+    }
+    c->density_cut = density_cut;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_bilateral_filter(tsplat_ctx *c, const float *in, float *out, int width, int height, float spatial_sigma,
+                                       float range_sigma, int kernel_size, void *stream)
+{
+    if (!c || !in || !out) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (in == out) return set_err(TSPLAT_ERR_INVALID, "in and out must differ");
+    if (width <= 0 || height <= 0 || kernel_size < 0 || kernel_size > 4096) return set_err(TSPLAT_ERR_INVALID, "bad size");
+    if (!(spatial_sigma > 0.0f) || !(range_sigma > 0.0f)) return set_err(TSPLAT_ERR_INVALID, "sigmas must be positive");
+    CUDA_TRY(cudaSetDevice(c->device));
+    tsplat_surface::BilateralArgs a;
+    a.in = in; a.out = out; a.width = width; a.height = height; a.spatial_sigma = spatial_sigma; a.range_sigma = range_sigma;
+    a.kernel_size = kernel_size;
+    dim3 grid((width + 31) / 32, (height + 7) / 8);
+    tsplat_surface::k_bilateral_filter<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    c->launches++;
+    c->last_stream = (cudaStream_t)stream;
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_surface_shade(tsplat_ctx *c, const float *smoothed, int res, const tsplat_surface_params *params,
+                                    const float *lut, int lut_w, void *out, int out_w, int out_h, int out_fmt, void *stream)
+{
+    if (!c || !smoothed || !params || !out) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (res <= 0 || out_w <= 0 || out_h <= 0) return set_err(TSPLAT_ERR_INVALID, "bad size");
+    if (out_fmt < TSPLAT_FMT_RGBA8 || out_fmt > TSPLAT_FMT_RGBA32F) return set_err(TSPLAT_ERR_INVALID, "bad output format");
+    if (params->material_colormap && (!lut || lut_w <= 0)) return set_err(TSPLAT_ERR_INVALID, "material colormap LUT missing");
+    CUDA_TRY(cudaSetDevice(c->device));
+    tsplat_surface::ShadeArgs a;
+    a.image = smoothed; a.res = res; a.p = *params; a.lut = lut; a.lut_w = lut_w; a.out = out; a.out_w = out_w; a.out_h = out_h;
+    a.out_fmt = out_fmt;
+    dim3 grid((out_w + 255) / 256, out_h);
+    k_surface_shade<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());

@@ -151,6 +151,33 @@ class SplatEngine:
                                          _ptr(out), out.shape[1], out.shape[0], out_fmt, _stream(self.device)))
         return out
 
+    # -- surface render mode --------------------------------------------------------------------------------------
+    def set_surface(self, lut: np.ndarray | None, density_cut: float):
+        """Local-sphere kernel LUT (None keeps the one already uploaded) and density cut of MODE_SURFACE renders."""
+        if lut is None:
+            N.check(self.lib.tsplat_set_surface(self._ctx, None, 0, ctypes.c_float(density_cut)))
+        else:
+            lut = np.ascontiguousarray(lut, dtype=np.float32)
+            N.check(self.lib.tsplat_set_surface(self._ctx, lut.ctypes.data_as(ctypes.c_void_p), lut.size, ctypes.c_float(density_cut)))
+
+    def bilateral_filter(self, image: torch.Tensor, out: torch.Tensor, spatial_sigma: float, range_sigma: float, kernel_size: int):
+        """Bilateral filter of channel 1 of an (H, W, 2) float32 image into ``out`` (channel 0 is copied)."""
+        if image.dim() != 3 or image.shape[2] != 2 or image.dtype != torch.float32 or not image.is_contiguous():
+            raise ValueError("Input array must be 3D with shape (height, width, 2), contiguous float32")
+        if out.shape != image.shape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("output must match the input")
+        N.check(self.lib.tsplat_bilateral_filter(self._ctx, _ptr(image), _ptr(out), image.shape[1], image.shape[0],
+                                                 ctypes.c_float(spatial_sigma), ctypes.c_float(range_sigma), int(kernel_size),
+                                                 _stream(self.device)))
+        return out
+
+    def surface_shade(self, smoothed: torch.Tensor, params: N.SurfaceParams, lut: torch.Tensor | None, out: torch.Tensor,
+                      out_fmt: int):
+        N.check(self.lib.tsplat_surface_shade(self._ctx, _ptr(smoothed), smoothed.shape[0], ctypes.byref(params), _ptr(lut),
+                                              0 if lut is None else lut.shape[0], _ptr(out), out.shape[1], out.shape[0],
+                                              out_fmt, _stream(self.device)))
+        return out
+
     # -- device-side autorange ------------------------------------------------------------------------------------
     def content_stats(self, image: torch.Tensor, content: int, scale: float) -> N.ContentStats:
         st = N.ContentStats()

@@ -52,3 +52,18 @@ def kernel_level(n_samples: int) -> np.ndarray:
 def kernel_lut() -> np.ndarray:
     """All four levels, row-major, concatenated: float32[5440] in the layout tsplat_set_kernel_lut expects."""
     return np.concatenate([kernel_level(n).astype(np.float32).ravel() for n in LEVEL_SIZES])
+
+
+def local_sphere_level(n_samples: int) -> np.ndarray:
+    """Surface mode's kernel image (reference: LocalSphereKernel, sph.py:446-455, sampled by _get_kernel_at_resolution with
+    normalisation 1.0, :497-501): depth of a sphere of radius 2h below its silhouette, -0.01 outside it (the fragment
+    shader discards negative samples)."""
+    centres = np.linspace(-2 + 2.0 / n_samples, 2 - 2.0 / n_samples, n_samples)
+    xx, yy = np.meshgrid(centres, centres)
+    d2 = xx ** 2 + yy ** 2
+    return np.where(np.sqrt(d2) < 2.0, np.sqrt(np.clip(4.0 - d2, 0.0, None)), -0.01)
+
+
+def local_sphere_lut() -> np.ndarray:
+    """float32[5440] in the layout tsplat_set_surface expects."""
+    return np.concatenate([local_sphere_level(n).astype(np.float32).ravel() for n in LEVEL_SIZES])

@@ -12,6 +12,7 @@ import logging
 
 import numpy as np
 
+from . import _native as N
 from . import split_buffers
 
 logger = logging.getLogger(__name__)
@@ -99,6 +100,15 @@ class ParticleBuffers:
             if len(starts) == 0 and not clear:
                 continue
             engine.set_particles(*pos_bufs[k])
-            engine.set_weights(*weight_bufs[k])
+            weights = weight_bufs[k]
+            if mode == N.MODE_SURFACE and weights[1] is None:
+                # no quantity selected: the reference's (m, q, 0) vertex buffer carries q = 0
+                if not hasattr(self, "_zero_quantity"):
+                    self._zero_quantity = {}
+                if k not in self._zero_quantity:
+                    import torch
+                    self._zero_quantity[k] = torch.zeros_like(weights[0])
+                weights = (weights[0], self._zero_quantity[k])
+            engine.set_weights(*weights)
             engine.render(mode, starts, lens, clear=clear, image=image)
             clear = False

@@ -9,6 +9,7 @@ behind ``tsplat_render`` (topsy_b200/csrc/tsplat.cu).
                        of ``get_image()`` is returned as zeros, as in the reference
   RGBSPH               (K r/h^2, K g/h^2, K b/h^2, fragment count)
   DepthSPH             (K m/h^2, K m/h^2 z_clip)  -> get_depth_image()
+  DepthSPHWithOcclusion  z-buffered (quantity, depth) of the front-most particles above a density cut ('surface' mode)
 """
 from __future__ import annotations
 
@@ -104,6 +105,11 @@ class SPH:
         self.last_transform_params = params
         self._engine.set_camera(np.ascontiguousarray(params["transform"].T), float(params["scale_factor"][0]))
 
+    def _reassert_engine_state(self):
+        """The engine is shared by every renderer at this resolution: re-assert our camera before adding blocks."""
+        self._engine.set_camera(np.ascontiguousarray(self.last_transform_params["transform"].T),
+                                float(self.last_transform_params["scale_factor"][0]))
+
     # -- rendering ------------------------------------------------------------------------------------------
     def invalidate(self, draw_reason=DrawReason.CHANGE):
         if draw_reason not in (DrawReason.REFINE, DrawReason.PRESENTATION_CHANGE):
@@ -119,9 +125,7 @@ class SPH:
             self._render_progression.select_sphere(-self.position_offset, self.scale * 1.2)
             self._update_transform_buffer()
         else:
-            # the engine is shared by every renderer at this resolution: re-assert our camera before adding blocks
-            self._engine.set_camera(np.ascontiguousarray(self.last_transform_params["transform"].T),
-                                    float(self.last_transform_params["scale_factor"][0]))
+            self._reassert_engine_state()
         self._last_mode = mode
         image = self._image_for_mode(mode)
         buffers = self._visualizer.particle_buffers
@@ -200,7 +204,49 @@ class DepthSPH(SPH):
 
 
 class DepthSPHWithOcclusion(SPH):
-    """Surface render mode (density cut + depth test).  Out of scope of the B200 hot path."""
+    """Renders the front-most particles above a density cut: per pixel (quantity, depth) of the fragment nearest to the
+    camera (reference: sph.py:457-601; vertex_depth_with_cut / fragment_raw, sph.wgsl:93-158).  The reference's depth
+    attachment + depth_compare=greater become one 64-bit atomic max per fragment on the (quantity, depth) pixel itself
+    (kernel K9, topsy_b200/csrc/tsplat_surface.cuh)."""
+    _nchannels_output = 2
+    _rho_percentiles_num_samples = 101      # the density cut is tabulated at every percentile from 0 to 100
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("render_mode='surface' is not implemented by topsy_b200 (outside the SPH projection path)")
+    def __init__(self, visualizer, render_resolution, wrapping=False, share_render_progression=None):
+        super().__init__(visualizer, render_resolution, wrapping, share_render_progression)
+        mass = self._visualizer.data_loader.get_mass()
+        smooth = self._visualizer.data_loader.get_smooth()
+        rho = mass / smooth ** 3
+        self._cut_min = np.log10(rho.min())
+        self._cut_max = np.log10(rho.max())
+        self._percentile_to_den_cut = np.quantile(rho, np.linspace(0, 1, self._rho_percentiles_num_samples))
+        self._cut_val = np.mean(self.get_density_cut_percentile_range())     # start at the median density
+        from .kernel_lut import local_sphere_lut
+        self._engine.set_surface(local_sphere_lut(), 0.0)
+
+    def _mode(self):
+        return N.MODE_SURFACE
+
+    def _get_transform_params(self):
+        tp = super()._get_transform_params()
+        tp["density_cut"] = self._percentile_to_den_cut[int(self._cut_val / 100.0 * (self._rho_percentiles_num_samples - 1))]
+        return tp
+
+    def _update_transform_buffer(self):
+        super()._update_transform_buffer()
+        self._engine.set_surface(None, float(self.last_transform_params["density_cut"][0]))
+
+    def _reassert_engine_state(self):
+        super()._reassert_engine_state()
+        self._engine.set_surface(None, float(self.last_transform_params["density_cut"][0]))
+
+    def get_density_cut_percentile(self):
+        return self._cut_val
+
+    def set_density_cut_percentile(self, value):
+        self._cut_val = value
+
+    def get_density_cut_percentile_range(self):
+        return 0.0, 100.0
+
+    def get_image(self):
+        return self._get_image_unscaled()       # maxima, not sums: no rescaling for partial renders

@@ -133,7 +133,8 @@ class VisualizerBase:
         params = self._get_colormap_parameters_for_render_mode(self._render_mode)
         changed_type = self._colormap.update_parameters(params)
         params = self._colormap.get_parameters()
-        show_colorbar = params['type'] not in ('rgb', 'surface')
+        show_colorbar = (params['type'] not in ('rgb', 'surface')
+                         or (params['type'] == 'surface' and params['weighted_average']))
         if changed_type or params['vmin'] is None or params['vmax'] is None:
             logger.info("Autorange colormap parameters")
             self._autorange()
