@@ -1,4 +1,4 @@
-"""Render-mode switching on the GPU (reference: tests/test_render_mode.py; 'surface' is outside the B200 hot path)."""
+"""Render-mode switching on the GPU (reference: tests/test_render_mode.py, same scenarios)."""
 import numpy as np
 import pytest
 
@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 import topsy_b200 as topsy
 from topsy_b200.canvas import offscreen
 
-MODES = ['univariate', 'bivariate', 'rgb', 'rgb-hdr']
+MODES = ['univariate', 'bivariate', 'rgb', 'rgb-hdr', 'surface']
 
 
 def check_outputs(vis, mode):
@@ -19,7 +19,7 @@ def check_outputs(vis, mode):
     assert pres.shape == (res, res, 4)
     if mode in ('rgb', 'rgb-hdr'):
         assert result.shape == (res, res, 3)
-    elif mode == 'bivariate':
+    elif mode in ('bivariate', 'surface'):
         assert result.shape == (res, res, 2)
     else:
         assert result.shape == (res, res)
@@ -60,9 +60,8 @@ def test_failed_switch_reverts():
         vis.render_mode = 'rgb-hdr'
     assert vis.render_mode == 'univariate'
     check_outputs(vis, 'univariate')
-    with pytest.raises(NotImplementedError):
-        vis.render_mode = 'surface'       # valid name in the reference, out of scope here: must also revert cleanly
-    assert vis.render_mode == 'univariate'
+    vis.render_mode = 'surface'           # a mode this canvas does support still switches afterwards
+    check_outputs(vis, 'surface')
 
 
 def test_unknown_quantity():
