@@ -52,7 +52,7 @@ constexpr int TILE_W = 64, TILE_H = 32;     // tile of the gather path (pixels):
 constexpr int MAX_RANGES = 1 << 16;         // ranges per render call (reference: <= n_cells = 4096 per buffer)
 constexpr int RANGE_SLOTS = 4;              // pinned staging ring for range tables
 constexpr float DIRECT_MAX_WPX = 8.0f;      // footprints up to this width are splatted by the projecting thread
-constexpr float HUGE_MIN_WPX = 256.0f;      // footprints above this go to the cooperative atomic kernel
+constexpr float HUGE_MIN_WPX = 4096.0f;     // footprints above this go to the cooperative atomic kernel (as does pair overflow)
 
 constexpr int STAT_SLOTS = 256;             // power of two
 struct StatSlot { unsigned long long culled_direct, reds; };   // culled in the low 32 bits, direct in the high 32
@@ -789,22 +789,11 @@ struct GatherSmem {
 };
 static_assert(sizeof(GatherSmem) * GATHER_CTAS_PER_SM <= 227 * 1024, "gather shared memory");
 
-// bilinear sample of the padded level 0 (row stride 65); bit-identical to sample_lut()'s magnification branch
-__device__ __forceinline__ float sample_bilinear_padded(const float *__restrict__ lut, float inv, float px0, float py1,
-                                                        float fx, float fy)
+__device__ __forceinline__ float lds_f32(unsigned addr)
 {
-    const float u = (fx - px0) * inv, v = (py1 - fy) * inv;
-    const float tu = fmaf(u, 64.0f, -0.5f), tv = fmaf(v, 64.0f, -0.5f);
-    const float iu = floorf(tu), iv = floorf(tv);
-    const float fu = tu - iu, fv = tv - iv;
-    const int a = (int)iu, b = (int)iv;
-    const int a0 = min(max(a, 0), 63), a1 = min(max(a + 1, 0), 63);
-    const int b0 = min(max(b, 0), 63), b1 = min(max(b + 1, 0), 63);
-    const float t00 = lut[b0 * 65 + a0], t01 = lut[b0 * 65 + a1];
-    const float t10 = lut[b1 * 65 + a0], t11 = lut[b1 * 65 + a1];
-    const float top = fmaf(fu, t01 - t00, t00);
-    const float bot = fmaf(fu, t11 - t10, t10);
-    return fmaf(fv, bot - top, top);
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));     // the LUT is read-only after the first barrier
+    return v;
 }
 
 // Eight LUT gathers of one lane, predicated on `p` (the lane's column is inside the footprint).  Lanes that are off do
@@ -979,7 +968,9 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                 nearest(ee.y, Kreg2);
             }
             if (i < nl) nearest(my_list[i], Kreg);
-            // bilinear records (back of the list; footprints of 64 px and more are rare): full sampler
+            // bilinear records (back of the list): footprints of 64 px and more magnify level 0.  The bilinear weights are
+            // separable too: the column part (two texel columns + fraction) is computed once per record, the row part
+            // per pixel row; same operations and FMA placement as sample_lut(), so results are bit-identical.
             const unsigned nlb = S.nlist[8 + warp];
             for (unsigned ib = 0; ib < nlb; ++ib) {
                 const unsigned r16 = my_list[G_BATCH - 1 - ib] & 0xfff0u;
@@ -988,13 +979,30 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                 const bool colok = fx >= A.x && fx < A.y;
                 float v1 = 0.0f, v2 = 0.0f;
                 if (C >= 2) { const float2 V = *reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(S.v) + (r16 >> 1)); v1 = V.x; v2 = V.y; }
+                const float inv = A.z;
+                const float tu = fmaf((fx - A.x) * inv, 64.0f, -0.5f);
+                const float iuf = floorf(tu);
+                const float fu = tu - iuf;
+                const int ia = (int)iuf;
+                const unsigned c0 = lut_sa + 4u * (unsigned)min(max(ia, 0), 63), c1 = lut_sa + 4u * (unsigned)min(max(ia + 1, 0), 63);
+                const float m0 = colok ? A.w : 0.0f, m1 = colok ? v1 : 0.0f, m2 = colok ? v2 : 0.0f;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const float fy = (float)(py0 + k) + 0.5f;
-                    if (colok && fy >= Y.x && fy < Y.y) {
-                        const float K = sample_bilinear_padded(S.lut, A.z, A.x, Y.y, fx, fy);
-                        gather_accumulate<MODE>(acc, k, K, A.w, v1, v2, 1.0f);
+                    const bool rowok = fy >= Y.x && fy < Y.y;
+                    const float tv = fmaf((Y.y - fy) * inv, 64.0f, -0.5f);
+                    const float ivf = floorf(tv);
+                    const float fv = tv - ivf;
+                    const int ib0 = (int)ivf;
+                    const unsigned r0 = 260u * (unsigned)min(max(ib0, 0), 63), r1 = 260u * (unsigned)min(max(ib0 + 1, 0), 63);
+                    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
+                    if (rowok) {                                       // rows are shared by a half-warp: near-uniform branch
+                        t00 = lds_f32(r0 + c0); t01 = lds_f32(r0 + c1); t10 = lds_f32(r1 + c0); t11 = lds_f32(r1 + c1);
                     }
+                    const float top = fmaf(fu, t01 - t00, t00);
+                    const float bot = fmaf(fu, t11 - t10, t10);
+                    const float K = fmaf(fv, bot - top, top);
+                    gather_accumulate<MODE>(acc, k, K, m0, m1, m2, (colok && rowok) ? 1.0f : 0.0f);
                 }
             }
         }
