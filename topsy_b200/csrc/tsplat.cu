@@ -774,15 +774,18 @@ struct GatherArgs {
 constexpr int PLUT_FLOATS = 7144;             // 4226 + 2*33*33 + 2*17*17 + 2*9*9
 __host__ __device__ constexpr int plut_base(int level) { return level == 0 ? 0 : level == 1 ? 4226 : level == 2 ? 6404 : 6982; }
 __host__ __device__ constexpr int plut_row_bytes(int level) { return level == 0 ? 260 : 8 * ((64 >> level) + 1); }
-constexpr int G_BATCH = 256;                  // records staged per round (one per thread)
-constexpr int GATHER_CTAS_PER_SM = 3;         // sizeof(GatherSmem) = 62 KB
+constexpr int G_BATCH = 128;                  // records staged per round
+constexpr int GATHER_CTAS_PER_SM = 3;         // sizeof(GatherSmem) = 70 KB
 
 struct GatherSmem {
     float lut[PLUT_FLOATS];
     float4 a[G_BATCH];                        // px0 px1 scale v0      (scale = inv * n, or inv when bilinear)
     float4 y[G_BATCH];                        // py0 py1 scale packed(level-base address | n << 16 | row bytes << 23)
     float2 v[G_BATCH];                        // v1 v2
-    unsigned short row[G_BATCH][TILE_H];      // shared-memory address of the LUT row of every tile row
+    // per (record, tile row) LUT row data, 256 bytes per record:
+    //   nearest-texel records use the first 64 bytes: 32 x u16 shared-memory address of the LUT row
+    //   bilinear records use all of it: 32 x { u32 address of texel row b0 | address of b1 << 16 | reuse flags, f32 fv }
+    uint2 row[G_BATCH][TILE_H];
     unsigned list[8][G_BATCH];                // per-warp record lists: record * 16 | n << 16   (n == 0: bilinear)
     unsigned nlist[16];                       // [0..7] nearest-texel entries (from the front), [8..15] bilinear (from the back)
     unsigned work[4];                         // tile, first pair, pair count
@@ -881,9 +884,11 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                 if (tid < 16) S.nlist[tid] = 0u;
                 __syncthreads();
             }
-            // ---- stage: one record per thread -------------------------------------------------------------
-            if ((unsigned)tid < nb) {
-                const unsigned ridx = a.pairs[first + b0 + tid];
+            // ---- stage: one record per lane 0..15; warp w owns records 16w .. 16w+15 of the batch, so that the row
+            // staging below only needs a warp-level barrier ---------------------------------------------------------
+            const unsigned rec = (unsigned)warp * 16u + (unsigned)lane;
+            if (lane < 16 && rec < nb) {
+                const unsigned ridx = a.pairs[first + b0 + rec];
                 const float4 q0 = reinterpret_cast<const float4 *>(a.queue + ridx)[0];      // px0 px1 py0 py1
                 const float4 q1 = reinterpret_cast<const float4 *>(a.queue + ridx)[1];      // wpx v0 v1 v2
                 const float wpx = q1.x, inv = 1.0f / wpx;
@@ -895,11 +900,11 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                     scale = inv * (float)n;
                     packed = (lut_sa + 4u * (unsigned)plut_base(level)) | (n << 16) | ((unsigned)plut_row_bytes(level) << 23);
                 }
-                S.a[tid] = make_float4(q0.x, q0.y, scale, q1.y);
-                S.y[tid] = make_float4(q0.z, q0.w, scale, __uint_as_float(packed));
-                if (C == 2) S.v[tid] = make_float2(q1.y * q1.z, 0.0f);       // (m/h^2) * (q | cz)
-                if (C == 4) S.v[tid] = make_float2(q1.z, q1.w);
-                const unsigned entry = ((unsigned)tid << 4) | (n << 16);
+                S.a[rec] = make_float4(q0.x, q0.y, scale, q1.y);
+                S.y[rec] = make_float4(q0.z, q0.w, scale, __uint_as_float(packed));
+                if (C == 2) S.v[rec] = make_float2(q1.y * q1.z, 0.0f);       // (m/h^2) * (q | cz)
+                if (C == 4) S.v[rec] = make_float2(q1.z, q1.w);
+                const unsigned entry = (rec << 4) | (n << 16);
                 // which of the 8 warp blocks (16 x 16 pixel centres each) does the record's span touch?
 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
@@ -910,18 +915,36 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                     }
                 }
             }
-            __syncthreads();
-            // ---- stage: LUT row address of every (record, tile row); lane = tile row ------------------------
+            __syncwarp();
+            // ---- stage: LUT row data of every (record, tile row) of the warp's own records; lane = tile row ----
             {
                 const float fy = tcy + (float)lane;
-                for (unsigned r = warp; r < nb; r += 8) {
+                const unsigned r_end = min(nb, (unsigned)warp * 16u + 16u);
+                for (unsigned r = (unsigned)warp * 16u; r < r_end; ++r) {
                     const float4 Y = S.y[r];
                     const unsigned packed = __float_as_uint(Y.w);
                     const int n = (int)((packed >> 16) & 127u);
+                    const bool ok = fy >= Y.x && fy < Y.y;
                     if (n) {
-                        const bool ok = fy >= Y.x && fy < Y.y;
                         const int iv = min(__float2int_rd((Y.y - fy) * Y.z), n - 1);
-                        S.row[r][lane] = (unsigned short)((packed & 0xffffu) + (unsigned)(ok ? iv : n) * (packed >> 23));
+                        reinterpret_cast<unsigned short *>(S.row[r])[lane] =
+                            (unsigned short)((packed & 0xffffu) + (unsigned)(ok ? iv : n) * (packed >> 23));
+                    } else {
+                        // bilinear on level 0 (row stride 260 bytes, row 64 is zero): the row half of sample_lut()
+                        const float tv = fmaf((Y.y - fy) * Y.z, 64.0f, -0.5f);
+                        const float ivf = floorf(tv);
+                        const int ib = (int)ivf;
+                        const unsigned a0 = lut_sa + 260u * (unsigned)(ok ? min(max(ib, 0), 63) : 64);
+                        const unsigned a1 = lut_sa + 260u * (unsigned)(ok ? min(max(ib + 1, 0), 63) : 64);
+                        // reuse flags for the lane that walks rows k-1, k in the same group of 8 (see the accumulate loop):
+                        // bit 15: both texel rows are those of the previous pixel row; bit 31: b1 is the previous row's b0
+                        const unsigned p0 = __shfl_up_sync(0xffffffffu, a0, 1), p1 = __shfl_up_sync(0xffffffffu, a1, 1);
+                        unsigned w = a0 | (a1 << 16);
+                        if ((lane & 7) != 0) {
+                            if (a0 == p0 && a1 == p1) w |= 0x8000u;
+                            else if (a1 == p0) w |= 0x80000000u;
+                        }
+                        S.row[r][lane] = make_uint2(w, __float_as_uint(tv - ivf));
                     }
                 }
             }
@@ -932,7 +955,7 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
                 const unsigned r16 = e & 0xfff0u;
                 const int n = (int)(e >> 16);
                 const float4 A = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.a) + r16);
-                const uint4 rw = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(S.row) + r16 * 4u + ly0 * 2);
+                const uint4 rw = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(S.row) + r16 * 16u + ly0 * 2);
                 const bool colok = fx >= A.x && fx < A.y;
                 float v1 = 0.0f, v2 = 0.0f;
                 if (C >= 2) { const float2 V = *reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(S.v) + (r16 >> 1)); v1 = V.x; v2 = V.y; }
@@ -969,40 +992,47 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
             }
             if (i < nl) nearest(my_list[i], Kreg);
             // bilinear records (back of the list): footprints of 64 px and more magnify level 0.  The bilinear weights are
-            // separable too: the column part (two texel columns + fraction) is computed once per record, the row part
-            // per pixel row; same operations and FMA placement as sample_lut(), so results are bit-identical.
+            // separable: the column part (two texel columns + fraction fu) is computed once per record by the lane, the
+            // row part (two texel rows + fraction fv) once per (record, tile row) while staging.  H(b) = lerp of texel row
+            // b at the lane's column; consecutive pixel rows mostly share texel rows (texel pitch >= 1 px), so H values
+            // are carried from row to row and only reloaded when the staged flags say so.  Same operations and FMA
+            // placement as sample_lut(): bit-identical samples.
             const unsigned nlb = S.nlist[8 + warp];
             for (unsigned ib = 0; ib < nlb; ++ib) {
                 const unsigned r16 = my_list[G_BATCH - 1 - ib] & 0xfff0u;
                 const float4 A = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.a) + r16);
-                const float4 Y = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(S.y) + r16);
                 const bool colok = fx >= A.x && fx < A.y;
                 float v1 = 0.0f, v2 = 0.0f;
                 if (C >= 2) { const float2 V = *reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(S.v) + (r16 >> 1)); v1 = V.x; v2 = V.y; }
-                const float inv = A.z;
-                const float tu = fmaf((fx - A.x) * inv, 64.0f, -0.5f);
+                const float tu = fmaf((fx - A.x) * A.z, 64.0f, -0.5f);
                 const float iuf = floorf(tu);
                 const float fu = tu - iuf;
                 const int ia = (int)iuf;
-                const unsigned c0 = lut_sa + 4u * (unsigned)min(max(ia, 0), 63), c1 = lut_sa + 4u * (unsigned)min(max(ia + 1, 0), 63);
+                const unsigned c0 = 4u * (unsigned)min(max(ia, 0), 63), c1 = 4u * (unsigned)min(max(ia + 1, 0), 63);
                 const float m0 = colok ? A.w : 0.0f, m1 = colok ? v1 : 0.0f, m2 = colok ? v2 : 0.0f;
+                const uint4 *rows = reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(S.row) + r16 * 16u + ly0 * 8);
+                float Htop = 0.0f, Hbot = 0.0f;
+                const uint4 rr4[4] = {rows[0], rows[1], rows[2], rows[3]};     // all 8 rows up front: one LDS latency, not four
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float fy = (float)(py0 + k) + 0.5f;
-                    const bool rowok = fy >= Y.x && fy < Y.y;
-                    const float tv = fmaf((Y.y - fy) * inv, 64.0f, -0.5f);
-                    const float ivf = floorf(tv);
-                    const float fv = tv - ivf;
-                    const int ib0 = (int)ivf;
-                    const unsigned r0 = 260u * (unsigned)min(max(ib0, 0), 63), r1 = 260u * (unsigned)min(max(ib0 + 1, 0), 63);
-                    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
-                    if (rowok) {                                       // rows are shared by a half-warp: near-uniform branch
-                        t00 = lds_f32(r0 + c0); t01 = lds_f32(r0 + c1); t10 = lds_f32(r1 + c0); t11 = lds_f32(r1 + c1);
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    const uint4 rr = rr4[k2];                           // two pixel rows: {w, fv} {w, fv}
+                    const unsigned ws[2] = {rr.x, rr.z};
+                    const float fvs[2] = {__uint_as_float(rr.y), __uint_as_float(rr.w)};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned w = ws[h];
+                        if (!(w & 0x8000u)) {                           // the pixel row needs (at least) a new top texel row
+                            const unsigned a0 = w & 0x7fffu, a1 = (w >> 16) & 0x7fffu;
+                            if (w & 0x80000000u) Hbot = Htop;
+                            else { const float t0 = lds_f32(a1 + c0), t1 = lds_f32(a1 + c1); Hbot = fmaf(fu, t1 - t0, t0); }
+                            const float t0 = lds_f32(a0 + c0), t1 = lds_f32(a0 + c1);
+                            Htop = fmaf(fu, t1 - t0, t0);
+                        }
+                        const float K = fmaf(fvs[h], Hbot - Htop, Htop);
+                        float cnt = 0.0f;
+                        if (C == 4) cnt = (colok && (w & 0x7fffu) != lut_sa + 260u * 64u) ? 1.0f : 0.0f;
+                        gather_accumulate<MODE>(acc, 2 * k2 + h, K, m0, m1, m2, cnt);
                     }
-                    const float top = fmaf(fu, t01 - t00, t00);
-                    const float bot = fmaf(fu, t11 - t10, t10);
-                    const float K = fmaf(fv, bot - top, top);
-                    gather_accumulate<MODE>(acc, k, K, m0, m1, m2, (colok && rowok) ? 1.0f : 0.0f);
                 }
             }
         }
