@@ -304,10 +304,9 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     reinterpret_cast<float2 *>(s_lut8w[warp])[lane] = lut_pair;
     unsigned n_culled = 0, n_direct = 0, n_deferred = 0;
     unsigned cells4 = 0;                          // cell counts of the lane's 4 particles, 8 bits each (<= 64)
+    unsigned defer_mask = 0;                      // which of the lane's 4 particles go to the deferred queue
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        bool defer = false;
-        float4 dq0 = make_float4(0.f, 0.f, 0.f, 0.f), dq1 = dq0;
         if (e >= e_first && e < e_last) {
             const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
             int j0, j1, k0, k1;
@@ -334,46 +333,57 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                     r.ncj = ncj;
                     r.magic = c_magic[ncj];
                 } else {
+                    // deferred: park the 32-byte queue record in the particle's own (otherwise unused) record slot;
+                    // it is copied to the global queue after ONE reservation per warp (below)
                     ++n_deferred;
-                    defer = true;
-                    dq0 = make_float4(p.px0, p.px1, p.py0, p.py1);
-                    dq1 = make_float4(p.wpx, v0, v1, v2);
+                    defer_mask |= 1u << e;
+                    DirectRec &r = s_rec[warp][e * 32 + lane];
+                    *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.px1, p.py0, p.py1);
+                    *reinterpret_cast<float4 *>(&r.v1) = make_float4(p.wpx, v0, v1, v2);
                 }
-            }
-        }
-        // warp-aggregated queue append: one global atomic per warp and e (a same-address ATOMG per particle serialises
-        // in the L2 once most particles are deferred)
-        const unsigned dm = __ballot_sync(0xffffffffu, defer);
-        if (dm) {
-            unsigned qb = 0;
-            if (lane == 0) qb = atomicAdd(&a.counters->q_count, (unsigned)__popc(dm));
-            qb = __shfl_sync(0xffffffffu, qb, 0);
-            const unsigned slot = qb + __popc(dm & lt_mask);
-            if (defer && slot < a.queue_cap) {
-                float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
-                q[0] = dq0;
-                q[1] = dq1;
             }
         }
     }
 
-    // one packed inclusive scan: low 16 bits = cells, high 16 bits = non-empty records
+    // one packed inclusive scan: bits 0-13 = cells (<= 8192), bits 14-22 = non-empty records (<= 128),
+    // bits 23-31 = deferred particles (<= 128)
     const unsigned c0 = cells4 & 0xffu, c1 = (cells4 >> 8) & 0xffu, c2 = (cells4 >> 16) & 0xffu, c3 = cells4 >> 24;
     const unsigned lane_cells = c0 + c1 + c2 + c3;
     const unsigned lane_recs = (c0 != 0u) + (c1 != 0u) + (c2 != 0u) + (c3 != 0u);
-    unsigned incl = lane_cells | (lane_recs << 16);
+    const unsigned lane_defer = (unsigned)__popc(defer_mask);
+    unsigned incl = lane_cells | (lane_recs << 14) | (lane_defer << 23);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
     const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned T = total & 0xffffu;
+    // queue append: ONE global atomic per warp (same-address atomics serialise in the L2 at ~1 per ns, which bounds
+    // this kernel as soon as most particles are deferred), then every lane copies its parked records
+    if (total >> 23) {
+        unsigned qb = 0;
+        if (lane == 0) qb = atomicAdd(&a.counters->q_count, total >> 23);
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+        unsigned slot = qb + (incl >> 23) - lane_defer;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (defer_mask & (1u << e)) {
+                if (slot < a.queue_cap) {
+                    const DirectRec &r = s_rec[warp][e * 32 + lane];
+                    float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
+                    q[0] = *reinterpret_cast<const float4 *>(&r.px0);
+                    q[1] = *reinterpret_cast<const float4 *>(&r.v1);
+                }
+                ++slot;
+            }
+        }
+    }
+    const unsigned T = total & 0x3fffu;
     const unsigned n_words = (T + 31u) >> 5;
     for (unsigned wi = lane; wi < n_words; wi += 32) s_bits[warp][wi] = 0u;
     __syncwarp();
     {
-        unsigned off = (incl & 0xffffu) - lane_cells, rank = (incl >> 16) - lane_recs;
+        unsigned off = (incl & 0x3fffu) - lane_cells, rank = ((incl >> 14) & 0x1ffu) - lane_recs;
         const unsigned cs[4] = {c0, c1, c2, c3};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
