@@ -55,6 +55,7 @@ constexpr float DIRECT_MAX_WPX = 8.0f;      // footprints up to this width are s
 constexpr float HUGE_MIN_WPX = 4096.0f;     // footprints above this go to the cooperative atomic kernel (as does pair overflow)
 
 constexpr int STAT_SLOTS = 256;             // power of two
+constexpr int PAIR_STRIPES = 32;            // power of two
 struct StatSlot { unsigned long long culled_direct, reds; };   // culled in the low 32 bits, direct in the high 32
 
 struct Counters {
@@ -62,10 +63,11 @@ struct Counters {
     StatSlot slots[STAT_SLOTS];  // K1's per-warp statistics land here (spread to avoid same-address atomics)
     unsigned int q_count;        // deferred records in the queue (this call)
     unsigned int huge_count;     // records routed to the cooperative atomic kernel (this call)
-    unsigned int pair_total;     // (particle, tile) pairs reserved (this call)
+    unsigned int pair_total;     // nonzero once any (particle, tile) pair was reserved (this call)
     unsigned int work_counter;   // persistent-kernel work ticket
     unsigned int n_segments;     // gather work units (this call)
     unsigned int pad;
+    unsigned int pair_sub[PAIR_STRIPES];   // pair-capacity reservations, striped: same-address atomics serialise in the L2
 };
 
 struct RangeTable {              // device layout of a multi-range call
@@ -598,11 +600,15 @@ __global__ void __launch_bounds__(1024) k_bin_count(const BinArgs a)
         }
         const unsigned warp_total = __shfl_sync(0xffffffffu, incl, 31);
         unsigned base = 0;
-        if (lane == 0 && warp_total) base = atomicAdd(&a.counters->pair_total, warp_total);
+        // capacity check only (positions come from the scan): each warp reserves from one of PAIR_STRIPES equal shares
+        if (lane == 0 && warp_total) {
+            base = atomicAdd(&a.counters->pair_sub[(blockIdx.x + (threadIdx.x >> 5)) & (PAIR_STRIPES - 1)], warp_total);
+            if (base == 0u) a.counters->pair_total = 1u;
+        }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (tiled) {
             const unsigned end = base + incl;
-            tiled = end <= a.pairs_cap && end >= base;
+            tiled = end <= a.pairs_cap / PAIR_STRIPES && end >= base;
         }
         if (valid) {
             unsigned route = 0;
@@ -1619,7 +1625,7 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
     if (blocks > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
     char *sc = static_cast<char *>(c->scratch);
     // per-call state: q_count .. pad, tile counters and cursors
-    CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, 6 * sizeof(unsigned int), st));
+    CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, (6 + PAIR_STRIPES) * sizeof(unsigned int), st));
     CUDA_TRY(cudaMemsetAsync(sc + L.tcount_off, 0, (size_t)(L.tcursor_off - L.tcount_off) * 2, st));
     if (blocks > 0) {
         // cell width of the vector REDs: as many pixels as fit 128 bits, if rows keep the cells aligned
@@ -1683,7 +1689,7 @@ static int launch_render_surface(tsplat_ctx *c, const ProjectArgs &pa, int64_t n
 {
     const int64_t blocks = (n_groups + 255) / 256;
     if (blocks > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
-    CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, 6 * sizeof(unsigned int), st));
+    CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, (6 + PAIR_STRIPES) * sizeof(unsigned int), st));
     if (blocks > 0) {
         ProjectArgs a2 = pa;
         a2.lut = c->d_slut;
