@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--particles", type=int, default=None, help="override particles per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--progressive", action="store_true",
+                    help="single GPU: also run the workload through the drop-in Visualizer with cells and report the "
+                         "interactive CHANGE + REFINE sequence (time to first frame, frames to complete, parity with EXPORT)")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl"], help="image sum method for N > 1")
     return ap.parse_args()
 
@@ -417,9 +420,91 @@ def run_ours(args):
                                     "sample": f"first {n_s} particles of the same workload, best of 3 ({secs:.2f} s each), "
                                               f"oracle/splat_oracle.c with fp32 accumulators",
                                     "os_cpu_count": os.cpu_count()}
+        if args.progressive and world == 1:
+            del data
+            sharded.close()
+            torch.cuda.empty_cache()
+            line["progressive"] = progressive_report(wl, n)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def progressive_report(wl, n):
+    """the same snapshot through Visualizer + ArrayDataLoader (cell layout, within-cell
+    shuffle, RenderProgressionWithCells): first interactive frame, REFINE frames until complete, parity with a one-shot
+    EXPORT render.  Host-side set-up (numpy cell layout of n particles) is reported separately and not part of a frame."""
+    import torch
+    from topsy_b200 import loader, synthetic
+    from topsy_b200.canvas import offscreen
+    from topsy_b200.drawreason import DrawReason
+    from topsy_b200.visualizer import Visualizer
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    data = synthetic.generate(wl, dev, n_total=n, n=n)
+    host = {k: v.cpu().numpy() for k, v in data.items()}
+    del data
+    torch.cuda.empty_cache()
+    pos = np.stack([host["x"], host["y"], host["z"]], axis=1)
+    kwargs = {"quantities": {"q": host["q"]}} if "q" in host else {}
+    if wl.mode == "rgb":
+        kwargs["rgb"] = np.stack([host["r"], host["g"], host["b"]], axis=1)
+    mass = host["m"] if "m" in host else np.ones(n, np.float32)
+    t0 = time.perf_counter()
+    vis = Visualizer(data_loader_class=loader.ArrayDataLoader, data_loader_args=(pos, host["h"], mass), data_loader_kwargs=kwargs,
+                     render_resolution=wl.resolution, canvas_class=offscreen.VisualizerCanvas,
+                     render_mode="rgb" if wl.mode == "rgb" else "univariate")
+    if "q" in host:
+        vis.quantity_name = "q"
+    vis.scale = wl.scale
+    vis.rotate(*wl.rotate)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    def timed(reason):
+        torch.cuda.synchronize(); a = time.perf_counter()
+        vis.render_sph(reason)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - a) * 1e3
+
+    timed(DrawReason.EXPORT)                              # warm-up (uploads the quantity buffer)
+    export_ms = timed(DrawReason.EXPORT)
+    ref = vis._sph.get_image().astype(np.float64)
+
+    def interactive_sequence():
+        vis.invalidate(DrawReason.CHANGE)
+        first_ms = timed(DrawReason.CHANGE)
+        fraction = 1.0 / float(vis._sph.last_render_mass_scale)
+        frames, refine_ms = 1, 0.0
+        while vis._sph.needs_refine() and frames < 10000:
+            refine_ms += timed(DrawReason.REFINE)
+            frames += 1
+        return {"first_frame_ms": first_ms, "first_frame_particle_fraction": fraction, "frames_to_complete": frames,
+                "refine_total_ms": refine_ms}
+
+    # cold start: the particle budget of a fresh progression (config.INITIAL_PARTICLES_TO_RENDER = 1e5), as after loading
+    rp = vis._sph._render_progression
+    rp._recommended_num_particles_to_render = min(int(1e5), n)
+    cold = interactive_sequence()
+    # adapted: the budget the progression has learned from the splat rate of the previous frames
+    warm = interactive_sequence()
+    first_ms, frames, refine_ms = warm["first_frame_ms"], warm["frames_to_complete"], warm["refine_total_ms"]
+    first_scale = 1.0 / warm["first_frame_particle_fraction"]
+    img = vis._sph.get_image().astype(np.float64)
+    # interactive frames draw only the cells selected by select_sphere(-offset, 1.2 * scale) (sph.py:313) while a one-block
+    # EXPORT frame draws every particle (progressive_render.py:197-198).  A particle inside the clip volume (|z| <= scale) at
+    # in-plane radius r is certainly selected if sqrt(r^2 + scale^2) <= 1.2 scale, i.e. r <= 0.66 scale: the two renders
+    # must agree inside that circle and differ outside it by construction (SURVEY section 8, quirk i)
+    R = ref.shape[0]
+    yy, xx = np.mgrid[0:R, 0:R]
+    inside = (xx - R / 2 + 0.5) ** 2 + (yy - R / 2 + 0.5) ** 2 <= (0.6 * R / 2) ** 2
+    worst = 0.0
+    for c in range(ref.shape[2]):
+        big = (np.abs(ref[..., c]) > 1e-6 * np.abs(ref[..., c]).max()) & inside
+        if big.any():
+            worst = max(worst, float(np.max(np.abs(img[..., c][big] - ref[..., c][big]) / np.abs(ref[..., c][big]))))
+    return {"host_setup_s": setup_s, "export_frame_ms": export_ms, "cold_start": cold, "adapted": warm, "max_rel_err_vs_export_within_0.6_scale": worst,
+            "path": "Visualizer + ArrayDataLoader (cells) -> render_sph(CHANGE) + render_sph(REFINE) until complete"}
 
 
 def main():

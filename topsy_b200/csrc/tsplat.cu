@@ -159,6 +159,7 @@ struct ProjectArgs {
     // single range (n_ranges == 1): particles [start, end); groups [g0, g0 + n_groups)
     int64_t start, end, g0, n_groups;
     int64_t n_total;             // particles in the buffers (the last 4-group may be partial)
+    int small_call;              // the call is too small for the tile binning: deferred records all go to K3b
     RangeTable table;            // used when table.n > 0
 };
 
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         const unsigned long long cd = (unsigned long long)(packed & 0xffu) | ((unsigned long long)((packed >> 8) & 0xffu) << 32);
         if (cd) atomicAdd(&slot->culled_direct, cd);
         if (T) atomicAdd(&slot->reds, (unsigned long long)T);   // cells walked = vector REDs issued (minus all-zero cells)
+        if (a.small_call && (packed >> 16)) atomicAdd(&a.counters->huge, (unsigned long long)(packed >> 16));
     }
 #endif
 }
@@ -1626,7 +1628,7 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
     char *sc = static_cast<char *>(c->scratch);
     // per-call state: q_count .. pad, tile counters and cursors
     CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, (6 + PAIR_STRIPES) * sizeof(unsigned int), st));
-    CUDA_TRY(cudaMemsetAsync(sc + L.tcount_off, 0, (size_t)(L.tcursor_off - L.tcount_off) * 2, st));
+    if (!pa.small_call) CUDA_TRY(cudaMemsetAsync(sc + L.tcount_off, 0, (size_t)(L.tcursor_off - L.tcount_off) * 2, st));
     if (blocks > 0) {
         // cell width of the vector REDs: as many pixels as fit 128 bits, if rows keep the cells aligned
         constexpr int CW = ModeTraits<MODE>::C == 1 ? 4 : ModeTraits<MODE>::C == 2 ? 2 : 1;
@@ -1634,7 +1636,15 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
         else k_project_splat<MODE, 1><<<(unsigned)blocks, threads, 0, st>>>(pa);
         c->launches++;
     }
-    if (pa.queue_cap > 0) {
+    if (pa.queue_cap > 0 && pa.small_call) {
+        // an interactive block of a few thousand particles: the binning machinery (4 more launches) costs more than it
+        // saves, k_bin_count would route every record to the cooperative atomic kernel anyway (Q < SMALL_QUEUE)
+        QueueArgs qa;
+        qa.queue = pa.queue; qa.indices = nullptr; qa.count = &c->d_counters->q_count; qa.cap = pa.queue_cap;
+        qa.lut = c->d_lut; qa.image = c->image; qa.R = c->R;
+        k_queue_atomic<MODE><<<c->sm_count * 8, 256, 0, st>>>(qa);
+        c->launches++;
+    } else if (pa.queue_cap > 0) {
         BinArgs ba;
         ba.queue = pa.queue; ba.queue_cap = pa.queue_cap; ba.counters = c->d_counters;
         ba.route = reinterpret_cast<unsigned char *>(sc + L.route_off);
@@ -1762,6 +1772,7 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
     auto submit = [&](const ProjectArgs &args, int64_t n_groups, int64_t n_particles) -> int {
         ProjectArgs a2 = args;
         a2.queue_cap = (unsigned)(chunk_cap < n_particles ? chunk_cap : n_particles);
+        a2.small_call = a2.queue_cap < SMALL_QUEUE;
         a2.n_groups = n_groups;
         switch (mode) {
         case TSPLAT_MODE_SURFACE: return launch_render_surface(c, a2, n_groups, st);

@@ -53,26 +53,24 @@ class SplitBuffers:
         return bufs, starts, lengths
 
     def global_to_split_monotonic(self, start, length):
-        """Per-buffer ``(starts, lengths)`` lists for monotonically increasing global ranges: one sweep instead of
-        one search per range (split_buffers.py:78-116).  Always returns ``num_buffers`` entries."""
+        """Per-buffer ``(starts, lengths)`` lists for monotonically increasing global ranges (split_buffers.py:78-116).
+        Always returns ``num_buffers`` entries.  The reference sweeps the ranges in a Python loop; this runs once per
+        render block with up to n_cells ranges, so it is vectorised: every buffer clips all ranges at once."""
         performance.signposter.emit_event("global_to_split_monotonic")
-        result = [([], []) for _ in range(self._num_buffers)]
-        buf = 0
-        buf_begin = 0
-        buf_end = self._buffer_particle_sizes[0]
-        for g_start, g_len in zip(start, length):
-            while g_len > 0:
-                while g_start >= buf_end:
-                    buf += 1
-                    if buf >= self._num_buffers:
-                        raise ValueError(f"Requested length {g_len} starting at {g_start} exceeds available buffers")
-                    buf_begin = self._buffer_particle_starts[buf]
-                    buf_end = buf_begin + self._buffer_particle_sizes[buf]
-                take = min(g_len, buf_end - g_start)
-                result[buf][0].append(g_start - buf_begin)
-                result[buf][1].append(take)
-                g_start += take
-                g_len -= take
+        start = np.asarray(start, dtype=np.int64).ravel()
+        end = start + np.asarray(length, dtype=np.int64).ravel()
+        live = end > start
+        if live.any() and end[live].max() > self._num_particles:
+            bad = int(np.argmax(live & (end > self._num_particles)))
+            raise ValueError(f"Requested length {int(end[bad] - start[bad])} starting at {int(start[bad])} exceeds available buffers")
+        result = []
+        for k in range(self._num_buffers):
+            b0 = int(self._buffer_particle_starts[k])
+            b1 = b0 + int(self._buffer_particle_sizes[k])
+            lo = np.maximum(start, b0)
+            n = np.minimum(end, b1) - lo
+            keep = n > 0
+            result.append(((lo[keep] - b0).tolist(), n[keep].tolist()))
         performance.signposter.emit_event("end global_to_split_monotonic")
         return result
 
