@@ -157,3 +157,29 @@ def test_uniform_box_parity(oracle_lut, mode, R, n, hscale):
         assert_image_parity(img, ref, f"uniform mode {mode}")
     finally:
         eng.close()
+
+
+def test_pair_capacity_overflow_falls_back_to_atomics(oracle_lut):
+    """250k footprints that each cover all 32 gather tiles of a 256^2 image: 8M (record, tile) pairs against a capacity of
+    6 per queue slot (striped over 32 reservation counters) -> part of the records must take the cooperative atomic path,
+    and the image must not change."""
+    from topsy_b200.engine import SplatEngine
+    rs = np.random.RandomState(3)
+    n, R = 250_000, 256
+    pos = rs.uniform(-0.2, 0.2, (n, 3)).astype(np.float32)
+    h = rs.uniform(0.8, 1.6, n).astype(np.float32)            # quad width 2 h R / scale = 410 .. 820 px
+    m = rs.uniform(0.5, 1.5, n).astype(np.float32)
+    M = o.transform_matrix(o.rotate(np.eye(3), 0.2, -0.3), np.zeros(3), 1.0); sf = o.scale_factor(1.0)
+    ref = co.splat(pos[:, 0], pos[:, 1], pos[:, 2], h, (m,), M, sf, R, o.MODE_DENSITY, oracle_lut)
+    eng = SplatEngine(R)
+    try:
+        eng.set_kernel_lut(oracle_lut)
+        eng.set_camera(M, sf)
+        x, y, z, hd, md = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], h, m)
+        eng.set_particles(x, y, z, hd); eng.set_weights(md)
+        img = eng.render(o.MODE_DENSITY).cpu().numpy()
+        st = eng.stats()
+        assert st["particles_huge"] > 0 and st["particles_tiled"] > 0, st      # both routes were taken
+        assert_image_parity(img, ref, "pair overflow")
+    finally:
+        eng.close()
