@@ -392,7 +392,8 @@ def run_ours(args):
             "phases_ms": {"splat": splat_ms_max, "reduce_and_colormap": present_ms},
             "roofline": {"bound": "hbm", "kernel": "k_project_splat (+ deferred queue kernels) per frame",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_frame": bytes_alg,
+                         "peak_source": peak_src, "frac_of_nominal_8000_GBs": achieved / 8000.0,
+                         "algorithmic_bytes_per_frame": bytes_alg,
                          "algorithmic_bytes_per_launch": min(n, 2 ** 25) * wl.bytes_per_particle,
                          "traffic": NCU_TRAFFIC_PER_LAUNCH.get(wl.name),
                          "traffic_source": "profiles/r01/k1_c4_dram_traffic_v5.txt (ncu dram__bytes_read+write per 2^25-particle launch)"

@@ -135,8 +135,11 @@ def test_empty_and_degenerate(engine200, oracle_lut):
     assert_image_parity(img, ref, "degenerate")
 
 
+# the last four cases defer > 131072 records, i.e. they go through the tile binning and the column-strip gather (K2 + K3)
+# in every mode, with a mix of nearest-texel (< 64 px) and bilinear (>= 64 px) footprints
 @pytest.mark.parametrize("mode,R,n,hscale", [(o.MODE_DENSITY, 512, 1_000_000, 0.002), (o.MODE_RGB, 1024, 2_000_000, 0.001),
-                                            (o.MODE_WEIGHTED, 256, 200_000, 0.05)])
+                                            (o.MODE_WEIGHTED, 256, 200_000, 0.05), (o.MODE_RGB, 256, 200_000, 0.1),
+                                            (o.MODE_DEPTH, 320, 200_000, 0.08), (o.MODE_DENSITY, 200, 200_000, 0.3)])
 def test_uniform_box_parity(oracle_lut, mode, R, n, hscale):
     """Larger seeded runs (the oracle's C/OpenMP restatement finishes in seconds)."""
     from topsy_b200.engine import SplatEngine
@@ -144,7 +147,7 @@ def test_uniform_box_parity(oracle_lut, mode, R, n, hscale):
     pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
     h = (hscale * np.exp(rs.normal(size=n) * 0.5)).astype(np.float32)
     w = [rs.uniform(0.1, 1.0, n).astype(np.float32) for _ in range(3)]
-    w = {o.MODE_DENSITY: w[:1], o.MODE_WEIGHTED: w[:2], o.MODE_RGB: w[:3]}[mode]
+    w = {o.MODE_DENSITY: w[:1], o.MODE_WEIGHTED: w[:2], o.MODE_RGB: w[:3], o.MODE_DEPTH: w[:1]}[mode]
     M = o.transform_matrix(o.rotate(np.eye(3), 0.3, 0.4), np.zeros(3), 1.0); sf = o.scale_factor(1.0)
     ref = co.splat(pos[:, 0], pos[:, 1], pos[:, 2], h, w, M, sf, R, mode, oracle_lut)
     eng = SplatEngine(R)

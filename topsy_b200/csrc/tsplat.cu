@@ -3,14 +3,18 @@
 //
 // Kernels
 //   K1  k_project_splat<MODE>   one pass over the SoA particle arrays (128-bit loads, 4 particles / thread):
-//                               rotate/project/cull, classify by projected footprint; small footprints are splatted
+//                               rotate/project/cull, classify by projected footprint; footprints up to 8 px are splatted
 //                               immediately with vector REDs (REDG.E.ADD.F32{,x2,x4}) into the L2-resident image,
-//                               larger ones are appended to a 32-byte projected-record queue.
-//   K2  k_bin_count / k_bin_scan / k_bin_fill      tile binning of the queue (16x16 pixel tiles)
-//   K3  k_tile_gather<MODE>     thread-per-pixel tiles, whole kernel LUT in shared memory, no atomics in the loop
-//   K3b k_queue_atomic<MODE>    cooperative (warp-per-particle) atomic splat for huge footprints / pair overflow
+//                               larger ones are appended to a 32-byte projected-record queue (one reservation per warp).
+//   K2  k_bin_count / k_bin_scan / k_bin_fill      counting sort of the queue by 64x32-pixel tile
+//   K3  k_tile_gather<MODE>     column strips in registers, LUT row addresses staged per (record, tile row),
+//                               whole kernel LUT in shared memory, no atomics in the loop
+//   K3b k_queue_atomic<MODE>    cooperative (warp / CTA per record) atomic splat: small calls, > 4096 px, pair overflow
 //   K5  k_colormap              fused normalise + log/linear + LUT (1-D / 2-D) or tri-band gamma map -> RGBA8/16F/32F
-//   K4  k_cell_*                CellLayout.from_positions: cell keys + stable counting sort
+//   K6  k_reduce_colormap       multi-GPU: image sum over NVLink peer memory fused with the colormap
+//   K7  k_periodic_accumulate   PeriodicSPH replica sum;  K8 k_content_stats / k_content_select  device autorange
+//   K9-K11 (tsplat_surface.cuh) surface mode: z-buffered splat, bilateral filter, lighting
+//   K4  k_cell_* (tsplat_cells.cu)  CellLayout.from_positions: cell keys + stable counting sort
 #include "tsplat_device.cuh"
 #include "../../include/tsplat.h"
 
