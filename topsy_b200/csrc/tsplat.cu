@@ -251,10 +251,17 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     // Warps are fully independent (no block-wide barrier): every warp stages its own copy of the 8x8 LUT level, and the
     // loads that feed it are issued together with the particle loads so that one memory latency covers both.
     __shared__ float s_lut8w[K1_WARPS][64];
-    __shared__ DirectRec s_rec[K1_WARPS][K1_RECS];
+    // record of (e, lane) lives at byte e * (32 * 48 + 32) + lane * 48 of the warp's slice: the 32-byte skew between the
+    // four e-blocks puts the four records of one lane -- consecutive in the flattened list, so read together by
+    // neighbouring lanes in phase B -- into different bank groups (without it they are 1536 bytes apart: same banks)
+    constexpr int K1_REC_BLOCK = 32 * (int)sizeof(DirectRec) + 32;
+    __shared__ __align__(16) unsigned char s_rec_raw[K1_WARPS][4 * K1_REC_BLOCK];
     __shared__ unsigned s_bits[K1_WARPS][K1_BITWORDS];
     __shared__ unsigned char s_slot[K1_WARPS][K1_RECS];      // rank among non-empty records -> record slot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto rec_at = [&](unsigned slot) -> DirectRec & {
+        return *reinterpret_cast<DirectRec *>(s_rec_raw[warp] + (slot >> 5) * K1_REC_BLOCK + (slot & 31u) * sizeof(DirectRec));
+    };
     const float2 lut_pair = __ldg(reinterpret_cast<const float2 *>(a.lut + lut_offset(3)) + lane);
     const uint64_t pol_stream = l2_policy_evict_first(), pol_image = l2_policy_evict_last();
     const float *s_lut8 = s_lut8w[warp];
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                     const int cj0 = j0 >> CELL_SHIFT;
                     const unsigned ncj = (unsigned)((j1 >> CELL_SHIFT) - cj0 + 1);
                     cells4 |= (ncj * (unsigned)(k1 - k0 + 1)) << (8 * e);
-                    DirectRec &r = s_rec[warp][e * 32 + lane];      // slot e*32+lane: conflict-free 128-bit stores
+                    DirectRec &r = rec_at(e * 32 + lane);           // slot e*32+lane: conflict-free 128-bit stores
                     *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.py1, 1.0f / p.wpx, v0);
                     *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)),
                                                                       __uint_as_float((unsigned)j0 | ((unsigned)j1 << 16)));
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                     // it is copied to the global queue after ONE reservation per warp (below)
                     ++n_deferred;
                     defer_mask |= 1u << e;
-                    DirectRec &r = s_rec[warp][e * 32 + lane];
+                    DirectRec &r = rec_at(e * 32 + lane);
                     *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.px1, p.py0, p.py1);
                     *reinterpret_cast<float4 *>(&r.v1) = make_float4(p.wpx, v0, v1, v2);
                 }
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         for (int e = 0; e < 4; ++e) {
             if (defer_mask & (1u << e)) {
                 if (slot < a.queue_cap) {
-                    const DirectRec &r = s_rec[warp][e * 32 + lane];
+                    const DirectRec &r = rec_at(e * 32 + lane);
                     float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
                     q[0] = *reinterpret_cast<const float4 *>(&r.px0);
                     q[1] = *reinterpret_cast<const float4 *>(&r.v1);
@@ -395,7 +402,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (cs[e]) {
-                s_rec[warp][e * 32 + lane].off = off;
+                rec_at(e * 32 + lane).off = off;
                 s_slot[warp][rank] = (unsigned char)(e * 32 + lane);
                 atomicOr(&s_bits[warp][off >> 5], 1u << (off & 31u));
                 off += cs[e];
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         const unsigned rk = rec_base + __popc(word & (lt_mask | (1u << lane))) - 1u;
         rec_base += __popc(word);
         if (t < T) {
-            const DirectRec &r = s_rec[warp][s_slot[warp][rk]];
+            const DirectRec &r = rec_at(s_slot[warp][rk]);
             const float4 ra = *reinterpret_cast<const float4 *>(&r.px0);      // px0 py1 inv v0
             const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk jj
             const uint4 rc = *reinterpret_cast<const uint4 *>(&r.off);        // off ncj magic pad
@@ -727,19 +734,34 @@ __global__ void __launch_bounds__(1024) k_bin_fill(const BinArgs a)
     const unsigned Q = min(a.counters->q_count, a.queue_cap);
     const unsigned per = (Q + gridDim.x - 1) / gridDim.x;
     const unsigned r0 = blockIdx.x * per, r1 = min(Q, r0 + per);
+    // both sweeps are latency-bound streaming reads of (route byte, first half of the record): four records per thread
+    // are loaded before any is processed
+    constexpr int UNROLL = 4;
+    auto sweep = [&](auto &&per_tile) {
+        for (unsigned rb = r0 + threadIdx.x; rb < r1; rb += UNROLL * blockDim.x) {
+            unsigned char route[UNROLL];
+            float4 q0[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const unsigned r = rb + u * blockDim.x;
+                route[u] = 0;
+                if (r < r1) { route[u] = a.route[r]; q0[u] = *reinterpret_cast<const float4 *>(a.queue + r); }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (route[u] != ROUTE_TILED) continue;
+                Deferred d; d.px0 = q0[u].x; d.px1 = q0[u].y; d.py0 = q0[u].z; d.py1 = q0[u].w;
+                int tx0, tx1, ty0, ty1;
+                tile_range(d, a.R, tx0, tx1, ty0, ty1);
+                for (int ty = ty0; ty <= ty1; ++ty)
+                    for (int tx = tx0; tx <= tx1; ++tx) per_tile(ty * a.ntx + tx, rb + u * blockDim.x);
+            }
+        }
+    };
     if (USE_SMEM) {
         for (int i = threadIdx.x; i < 2 * a.nt; i += blockDim.x) s_mem[i] = 0u;
         __syncthreads();
-        for (unsigned r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-            const unsigned char route = a.route[r];
-            const float4 q0 = *reinterpret_cast<const float4 *>(a.queue + r);     // issued with the route load, not after it
-            if (route != ROUTE_TILED) continue;
-            Deferred d; d.px0 = q0.x; d.px1 = q0.y; d.py0 = q0.z; d.py1 = q0.w;
-            int tx0, tx1, ty0, ty1;
-            tile_range(d, a.R, tx0, tx1, ty0, ty1);
-            for (int ty = ty0; ty <= ty1; ++ty)
-                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cur[ty * a.ntx + tx], 1u);
-        }
+        sweep([&](int t, unsigned) { atomicAdd(&s_cur[t], 1u); });
         __syncthreads();
         for (int i = threadIdx.x; i < a.nt; i += blockDim.x) {
             const unsigned v = s_cur[i];
@@ -748,20 +770,10 @@ __global__ void __launch_bounds__(1024) k_bin_fill(const BinArgs a)
         }
         __syncthreads();
     }
-    for (unsigned r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-        const unsigned char route = a.route[r];
-        const float4 q0 = *reinterpret_cast<const float4 *>(a.queue + r);
-        if (route != ROUTE_TILED) continue;
-        Deferred d; d.px0 = q0.x; d.px1 = q0.y; d.py0 = q0.z; d.py1 = q0.w;
-        int tx0, tx1, ty0, ty1;
-        tile_range(d, a.R, tx0, tx1, ty0, ty1);
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) {
-                const int t = ty * a.ntx + tx;
-                if (USE_SMEM) a.pairs[s_base[t] + atomicAdd(&s_cur[t], 1u)] = r;
-                else a.pairs[a.tile_offset[t] + atomicAdd(&a.tile_cursor[t], 1u)] = r;
-            }
-    }
+    sweep([&](int t, unsigned r) {
+        if (USE_SMEM) a.pairs[s_base[t] + atomicAdd(&s_cur[t], 1u)] = r;
+        else a.pairs[a.tile_offset[t] + atomicAdd(&a.tile_cursor[t], 1u)] = r;
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1677,11 +1689,11 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
             }
             k_bin_count<true><<<bin_grid, 1024, hist_bytes, st>>>(ba);
             k_bin_scan<<<1, 1024, 0, st>>>(ba);
-            k_bin_fill<true><<<bin_grid, 1024, 2 * hist_bytes, st>>>(ba);
+            k_bin_fill<true><<<c->sm_count, 1024, 2 * hist_bytes, st>>>(ba);
         } else {
             k_bin_count<false><<<bin_grid, 1024, 0, st>>>(ba);
             k_bin_scan<<<1, 1024, 0, st>>>(ba);
-            k_bin_fill<false><<<bin_grid, 1024, 0, st>>>(ba);
+            k_bin_fill<false><<<c->sm_count, 1024, 0, st>>>(ba);
         }
         GatherArgs ga;
         ga.queue = pa.queue; ga.pairs = ba.pairs; ga.tile_offset = ba.tile_offset; ga.seg_prefix = ba.seg_prefix;
