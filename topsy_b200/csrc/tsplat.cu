@@ -237,11 +237,10 @@ struct __align__(16) DirectRec {
     float px0, py1, inv, v0;
     float v1, v2;
     unsigned cjk;        // first cell column (low 16) | first row k0 (high 16)
-    unsigned jj;         // first covered pixel column j0 (low 16) | last j1 (high 16)
-    unsigned off;        // offset of the particle's first cell in the warp's flattened list
-    unsigned ncj;        // cell columns
-    unsigned magic;      // c_magic[ncj]
-    unsigned pad;
+    unsigned offn;       // offset of the first cell in the warp's flattened list (bits 0-12) | cell columns - 1 (13-15) |
+                         // c_magic[cell columns] & 0xffff (16-31; unused for one column)
+    unsigned jj;         // CELL_W > 1 only: first covered pixel column j0 (low 16) | last j1 (high 16)
+    unsigned pad[3];
 };
 
 template <int MODE, int CELL_W>
@@ -319,6 +318,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     unsigned n_culled = 0, n_direct = 0, n_deferred = 0;
     unsigned cells4 = 0;                          // cell counts of the lane's 4 particles, 8 bits each (<= 64)
     unsigned defer_mask = 0;                      // which of the lane's 4 particles go to the deferred queue
+    unsigned ncj4 = 0;                            // (cell columns - 1) of the lane's 4 direct particles, 4 bits each
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         if (e >= e_first && e < e_last) {
@@ -342,10 +342,9 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                     cells4 |= (ncj * (unsigned)(k1 - k0 + 1)) << (8 * e);
                     DirectRec &r = rec_at(e * 32 + lane);           // slot e*32+lane: conflict-free 128-bit stores
                     *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.py1, 1.0f / p.wpx, v0);
-                    *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)),
-                                                                      __uint_as_float((unsigned)j0 | ((unsigned)j1 << 16)));
-                    r.ncj = ncj;
-                    r.magic = c_magic[ncj];
+                    *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)), 0.0f);
+                    if (CELL_W > 1) r.jj = (unsigned)j0 | ((unsigned)j1 << 16);
+                    ncj4 |= (ncj - 1u) << (4 * e);
                 } else {
                     // deferred: park the 32-byte queue record in the particle's own (otherwise unused) record slot;
                     // it is copied to the global queue after ONE reservation per warp (below)
@@ -402,7 +401,8 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (cs[e]) {
-                rec_at(e * 32 + lane).off = off;
+                const unsigned ncj1 = (ncj4 >> (4 * e)) & 7u;
+                rec_at(e * 32 + lane).offn = off | (ncj1 << 13) | (c_magic[ncj1 + 1u] << 16);
                 s_slot[warp][rank] = (unsigned char)(e * 32 + lane);
                 atomicOr(&s_bits[warp][off >> 5], 1u << (off & 31u));
                 off += cs[e];
@@ -422,12 +422,11 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         if (t < T) {
             const DirectRec &r = rec_at(s_slot[warp][rk]);
             const float4 ra = *reinterpret_cast<const float4 *>(&r.px0);      // px0 py1 inv v0
-            const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk jj
-            const uint4 rc = *reinterpret_cast<const uint4 *>(&r.off);        // off ncj magic pad
-            const unsigned cjk = __float_as_uint(rb.z), jj = __float_as_uint(rb.w);
-            const unsigned local = t - rc.x;
-            const unsigned dk = (local * rc.z) >> 16;
-            const unsigned dc = local - dk * rc.y;
+            const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk off|ncj-1|magic
+            const unsigned cjk = __float_as_uint(rb.z), offn = __float_as_uint(rb.w);
+            const unsigned local = t - (offn & 0x1fffu), ncj1 = (offn >> 13) & 7u;
+            const unsigned dk = ncj1 ? (local * (offn >> 16)) >> 16 : local;
+            const unsigned dc = local - dk * (ncj1 + 1u);
             const unsigned k = (cjk >> 16) + dk;
             const unsigned cj = (cjk & 0xffffu) + dc;
             const float fy = (float)k + 0.5f;
@@ -442,7 +441,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                     else red_v2(a.image + 2 * (size_t)pix, val, val * rb.x, pol_image);
                 }
             } else {
-                const unsigned j0 = jj & 0xffffu, j1 = jj >> 16;
+                const unsigned jj = r.jj, j0 = jj & 0xffffu, j1 = jj >> 16;
                 float Ks[CELL_W];
                 bool any = false;
 #pragma unroll
