@@ -399,10 +399,12 @@ def run_ours(args):
                          "traffic_source": "profiles/r01/k1_c4_dram_traffic_v5.txt (ncu dram__bytes_read+write per 2^25-particle launch)"
                          if wl.name in NCU_TRAFFIC_PER_LAUNCH else None,
                          "bytes_per_particle": wl.bytes_per_particle},
-            "atomic_roofline": {"bound": "vector RED issue rate (SM-side L1TEX limit; profiles/r01/atomics_bench_b200.txt)",
+            "atomic_roofline": {"bound": "vector RED lane rate of the SM's LSU/L1TEX pipe, measured for lanes grouped in 2x2 pixel "
+                                         "quads like this workload's footprints (profiles/r01/red_patterns_b200.txt: 2.38e11 lanes/s; "
+                                         "1.84e11 fully scattered, 3.5e11 fully coalesced rows)",
                                 "direct_vector_reds_per_frame": int(st["direct_vector_reds"]),
-                                "achieved": st["direct_vector_reds"] / (splat_ms_max * 1e-3), "peak": 1.9e11, "unit": "RED lanes/s",
-                                "frac": st["direct_vector_reds"] / (splat_ms_max * 1e-3) / 1.9e11,
+                                "achieved": st["direct_vector_reds"] / (splat_ms_max * 1e-3), "peak": 2.38e11, "unit": "RED lanes/s",
+                                "frac": st["direct_vector_reds"] / (splat_ms_max * 1e-3) / 2.38e11,
                                 "reds_per_particle": st["direct_vector_reds"] / max(n, 1)},
             "gpu_launches": int(launches),
             "stats": {k: int(v) for k, v in st.items()},
