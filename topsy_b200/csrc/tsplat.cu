@@ -228,17 +228,14 @@ constexpr int K1_THREADS = 128;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_RECS = 128;                 // records per warp batch (4 per lane)
 constexpr int K1_MAX_SPAN = 8;               // direct particles cover at most 8 x 8 pixel centres
-constexpr int K1_BITWORDS = K1_RECS * K1_MAX_SPAN * K1_MAX_SPAN / 32;
-
-// (t * c_magic[n]) >> 16 == t / n for t < 4096, n in 1..8      (ceil(65536 / n))
-__constant__ unsigned c_magic[9] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u};
+constexpr int K1_BITWORDS = K1_RECS * K1_MAX_SPAN * (K1_MAX_SPAN / 2) / 32;     // work items: (cell column, row pair)
 
 struct __align__(16) DirectRec {
     float px0, py1, inv, v0;
     float v1, v2;
     unsigned cjk;        // first cell column (low 16) | first row k0 (high 16)
-    unsigned offn;       // offset of the first cell in the warp's flattened list (bits 0-12) | cell columns - 1 (13-15) |
-                         // c_magic[cell columns] & 0xffff (16-31; unused for one column)
+    unsigned offn;       // offset of the first work item in the warp's flattened list (bits 0-12) | cell columns - 1
+                         // (13-15) | rows - 1 (16-18)
     unsigned jj;         // CELL_W > 1 only: first covered pixel column j0 (low 16) | last j1 (high 16)
     unsigned pad[3];
 };
@@ -316,9 +313,10 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
 
     reinterpret_cast<float2 *>(s_lut8w[warp])[lane] = lut_pair;
     unsigned n_culled = 0, n_direct = 0, n_deferred = 0;
-    unsigned cells4 = 0;                          // cell counts of the lane's 4 particles, 8 bits each (<= 64)
+    unsigned cells4 = 0;                          // work items of the lane's 4 particles, 8 bits each (<= 32)
+    unsigned n_reds = 0;                          // cells = vector REDs of the lane's 4 particles
     unsigned defer_mask = 0;                      // which of the lane's 4 particles go to the deferred queue
-    unsigned ncj4 = 0;                            // (cell columns - 1) of the lane's 4 direct particles, 4 bits each
+    unsigned ncj4 = 0;                            // (cell columns - 1) | (rows - 1) << 3 of the lane's 4 direct particles, 8 bits each
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         if (e >= e_first && e < e_last) {
@@ -339,12 +337,14 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
                     ++n_direct;
                     const int cj0 = j0 >> CELL_SHIFT;
                     const unsigned ncj = (unsigned)((j1 >> CELL_SHIFT) - cj0 + 1);
-                    cells4 |= (ncj * (unsigned)(k1 - k0 + 1)) << (8 * e);
+                    const unsigned nrows = (unsigned)(k1 - k0 + 1);
+                    cells4 |= (ncj * ((nrows + 1u) >> 1)) << (8 * e);          // work items: (cell column, row pair)
+                    n_reds += ncj * nrows;
                     DirectRec &r = rec_at(e * 32 + lane);           // slot e*32+lane: conflict-free 128-bit stores
                     *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.py1, 1.0f / p.wpx, v0);
                     *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)), 0.0f);
                     if (CELL_W > 1) r.jj = (unsigned)j0 | ((unsigned)j1 << 16);
-                    ncj4 |= (ncj - 1u) << (4 * e);
+                    ncj4 |= ((ncj - 1u) | ((nrows - 1u) << 3)) << (8 * e);
                 } else {
                     // deferred: park the 32-byte queue record in the particle's own (otherwise unused) record slot;
                     // it is copied to the global queue after ONE reservation per warp (below)
@@ -401,8 +401,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (cs[e]) {
-                const unsigned ncj1 = (ncj4 >> (4 * e)) & 7u;
-                rec_at(e * 32 + lane).offn = off | (ncj1 << 13) | (c_magic[ncj1 + 1u] << 16);
+                rec_at(e * 32 + lane).offn = off | (((ncj4 >> (8 * e)) & 63u) << 13);
                 s_slot[warp][rank] = (unsigned char)(e * 32 + lane);
                 atomicOr(&s_bits[warp][off >> 5], 1u << (off & 31u));
                 off += cs[e];
@@ -422,44 +421,52 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
         if (t < T) {
             const DirectRec &r = rec_at(s_slot[warp][rk]);
             const float4 ra = *reinterpret_cast<const float4 *>(&r.px0);      // px0 py1 inv v0
-            const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk off|ncj-1|magic
+            const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk off|ncj-1|rows-1
             const unsigned cjk = __float_as_uint(rb.z), offn = __float_as_uint(rb.w);
-            const unsigned local = t - (offn & 0x1fffu), ncj1 = (offn >> 13) & 7u;
-            const unsigned dk = ncj1 ? (local * (offn >> 16)) >> 16 : local;
-            const unsigned dc = local - dk * (ncj1 + 1u);
-            const unsigned k = (cjk >> 16) + dk;
+            const unsigned local = t - (offn & 0x1fffu), ncj = ((offn >> 13) & 7u) + 1u, nrows1 = (offn >> 16) & 7u;
+            // a work item is one cell column x two rows: the record is fetched once for two REDs, and neighbouring lanes
+            // still hold horizontally adjacent cells, which share sectors in the RED path
+            const unsigned dk2 = (unsigned)(local >= ncj) + (unsigned)(local >= 2u * ncj) + (unsigned)(local >= 3u * ncj);
+            const unsigned dc = local - dk2 * ncj;
             const unsigned cj = (cjk & 0xffffu) + dc;
-            const float fy = (float)k + 0.5f;
-            const unsigned pix = k * (unsigned)a.R + cj * CELL_W;             // R <= 32768: fits 32 bits
-            if (CELL_W == 1) {
-                const float K = sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)cj + 0.5f, fy);
-                if (MODE == TSPLAT_MODE_RGB) {                       // RGB counts fragments even where K == 0
-                    red_v4(a.image + 4 * (size_t)pix, ra.w * K, rb.x * K, rb.y * K, 1.0f, pol_image);
-                } else if (K != 0.0f) {                              // adding +0 is a no-op
-                    const float val = K * ra.w;
-                    if (MODE == TSPLAT_MODE_DENSITY) red_v1(a.image + pix, val, pol_image);
-                    else red_v2(a.image + 2 * (size_t)pix, val, val * rb.x, pol_image);
-                }
-            } else {
-                const unsigned jj = r.jj, j0 = jj & 0xffffu, j1 = jj >> 16;
-                float Ks[CELL_W];
-                bool any = false;
+            unsigned jj = 0;
+            if (CELL_W > 1) jj = r.jj;
+            auto emit = [&](const unsigned k) {
+                const float fy = (float)k + 0.5f;
+                const unsigned pix = k * (unsigned)a.R + cj * CELL_W;         // R <= 32768: fits 32 bits
+                if (CELL_W == 1) {
+                    const float K = sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)cj + 0.5f, fy);
+                    if (MODE == TSPLAT_MODE_RGB) {                       // RGB counts fragments even where K == 0
+                        red_v4(a.image + 4 * (size_t)pix, ra.w * K, rb.x * K, rb.y * K, 1.0f, pol_image);
+                    } else if (K != 0.0f) {                              // adding +0 is a no-op
+                        const float val = K * ra.w;
+                        if (MODE == TSPLAT_MODE_DENSITY) red_v1(a.image + pix, val, pol_image);
+                        else red_v2(a.image + 2 * (size_t)pix, val, val * rb.x, pol_image);
+                    }
+                } else {
+                    const unsigned j0 = jj & 0xffffu, j1 = jj >> 16;
+                    float Ks[CELL_W];
+                    bool any = false;
 #pragma unroll
-                for (int c = 0; c < CELL_W; ++c) {
-                    const unsigned j = cj * CELL_W + c;
-                    const bool in = (j >= j0) && (j <= j1);
-                    Ks[c] = in ? sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)j + 0.5f, fy) : 0.0f;
-                    any |= (Ks[c] != 0.0f);
-                }
-                if (any) {
-                    if (MODE == TSPLAT_MODE_DENSITY) {
-                        red_v4(a.image + pix, Ks[0] * ra.w, Ks[1] * ra.w, Ks[2 % CELL_W] * ra.w, Ks[3 % CELL_W] * ra.w, pol_image);
-                    } else {                                  // two pixels x (val, val * q|cz)
-                        const float a0 = Ks[0] * ra.w, a1 = Ks[1] * ra.w;
-                        red_v4(a.image + 2 * (size_t)pix, a0, a0 * rb.x, a1, a1 * rb.x, pol_image);
+                    for (int c = 0; c < CELL_W; ++c) {
+                        const unsigned j = cj * CELL_W + c;
+                        const bool in = (j >= j0) && (j <= j1);
+                        Ks[c] = in ? sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)j + 0.5f, fy) : 0.0f;
+                        any |= (Ks[c] != 0.0f);
+                    }
+                    if (any) {
+                        if (MODE == TSPLAT_MODE_DENSITY) {
+                            red_v4(a.image + pix, Ks[0] * ra.w, Ks[1] * ra.w, Ks[2 % CELL_W] * ra.w, Ks[3 % CELL_W] * ra.w, pol_image);
+                        } else {                                  // two pixels x (val, val * q|cz)
+                            const float a0 = Ks[0] * ra.w, a1 = Ks[1] * ra.w;
+                            red_v4(a.image + 2 * (size_t)pix, a0, a0 * rb.x, a1, a1 * rb.x, pol_image);
+                        }
                     }
                 }
-            }
+            };
+            const unsigned k = (cjk >> 16) + 2u * dk2;
+            emit(k);
+            if (2u * dk2 < nrows1) emit(k + 1u);
         }
     }
 
@@ -467,12 +474,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     // serialisation in the L2 (tsplat_get_stats sums the slots)
     unsigned packed = n_culled | (n_direct << 8) | (n_deferred << 16);        // each <= 4 per lane, <= 128 per warp
     for (int d = 16; d > 0; d >>= 1) packed += __shfl_down_sync(0xffffffffu, packed, d);
+    const unsigned warp_reds = __reduce_add_sync(0xffffffffu, n_reds);
 #ifndef TSPLAT_NO_STATS
     if (lane == 0) {
         StatSlot *slot = a.counters->slots + ((blockIdx.x * K1_WARPS + warp) & (STAT_SLOTS - 1));
         const unsigned long long cd = (unsigned long long)(packed & 0xffu) | ((unsigned long long)((packed >> 8) & 0xffu) << 32);
         if (cd) atomicAdd(&slot->culled_direct, cd);
-        if (T) atomicAdd(&slot->reds, (unsigned long long)T);   // cells walked = vector REDs issued (minus all-zero cells)
+        if (warp_reds) atomicAdd(&slot->reds, (unsigned long long)warp_reds);   // cells = vector REDs issued (minus all-zero cells)
         if (a.small_call && (packed >> 16)) atomicAdd(&a.counters->huge, (unsigned long long)(packed >> 16));
     }
 #endif
