@@ -28,10 +28,11 @@ class CellLayout:
         """A permutation of 0..N-1 that shuffles particles uniformly inside each cell and never across cells, so that
         any leading fraction of a cell is a fair subsample (cell_layout.py:17-24; unseeded, like the reference)."""
         total = int(self._lengths.sum())
-        cell_of_slot = np.repeat(np.arange(len(self._lengths)), self._lengths)
-        shuffle_key = np.random.random(total)
-        # slots are already grouped by cell, so sorting by (cell, random key) permutes inside each group only
-        return np.lexsort((shuffle_key, cell_of_slot)).astype(np.uintp)
+        cell_of_slot = np.repeat(np.arange(len(self._lengths), dtype=_key_dtype(len(self._lengths))), self._lengths)
+        # a uniform permutation of all slots, regrouped by cell with a STABLE sort: inside every cell the slots keep the
+        # (uniformly random) relative order they have in the permutation.  O(N): numpy radix-sorts 16-bit keys.
+        perm = np.random.permutation(total)
+        return perm[np.argsort(cell_of_slot[perm], kind='stable')].astype(np.uintp)
 
     def cells_in_sphere(self, centre, radius: float) -> np.ndarray:
         """Indices of the cells whose centre lies within radius + one cell diagonal of ``centre`` (:26-31)."""
@@ -89,7 +90,8 @@ class CellLayout:
         if ijk.min() < 0 or ijk.max() >= nside:
             raise ValueError("Particle positions are too close to edge of box; expand box size")
         cell = ijk[:, 2] + nside * (ijk[:, 1] + nside * ijk[:, 0])
-        ordering = np.argsort(cell, kind='stable')
+        # same result as a stable argsort of the intp keys; 16-bit keys take numpy's O(N) radix sort
+        ordering = np.argsort(cell.astype(_key_dtype(nside ** 3), copy=False), kind='stable')
         lengths = np.bincount(cell, minlength=nside ** 3)
         assert len(lengths) == len(centres)
         offsets = np.cumsum(lengths) - lengths
@@ -137,6 +139,10 @@ class CellLayout:
         lengths_h = lengths.cpu().numpy().astype(np.intp)
         offsets = np.cumsum(lengths_h) - lengths_h
         return cls(centres, offsets, lengths_h), order
+
+
+def _key_dtype(n_cells: int):
+    return np.int16 if n_cells <= 32767 else np.intp
 
 
 def _is_cuda_tensor(obj) -> bool:
