@@ -175,7 +175,8 @@ int tsplat_surface_shade(tsplat_ctx *ctx, const float *smoothed, int res, const 
 
 /* Device-side autorange (replaces the host read-back + np.percentile of colormap/implementation.py:381-425,
  * :512-531, :576-588).  "content" selects what the colormap looks at: 0 = channel 0 * scale (density), 1 = channel 1 /
- * channel 0 (weighted mean), 2 = every channel * scale (RGB maps, which include the count channel like the reference).
+ * channel 0 (weighted mean), 2 = every channel * scale (RGB maps, which include the count channel like the reference),
+ * 3 = channel 0 * scale of the pixels whose channel 1 is positive (surface maps, colormap/surface.py:256-259).
  * tsplat_content_stats: finite min/max of the values and of their log10, whether any value is negative, counts.
  * tsplat_content_select: exact order statistics (0-based ranks among the finite values, ascending) of the values or of
  * their log10 -- a 3-pass radix select; the host interpolates percentiles from them like np.percentile.

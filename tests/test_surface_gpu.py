@@ -170,3 +170,14 @@ def test_surface_shade_matches_oracle_any_output_size():
             npt.assert_allclose(out.cpu().numpy(), want, atol=2e-4, err_msg=f"{ow}x{oh} colormap={colormap}")
     finally:
         eng.close()
+
+
+def test_surface_autorange_on_device_matches_host():
+    vis = topsy.test(50000, render_resolution=200, canvas_class=offscreen.VisualizerCanvas, render_mode='surface')
+    vis.scale = 40.0
+    vis.quantity_name = "test-quantity"        # autoranges on the device (Visualizer.use_device_autorange)
+    dev = {k: vis.colormap.get_parameter(k) for k in ("vmin", "vmax", "log")}
+    vis.colormap.autorange(vis._sph.get_image())   # the reference's host path on the same image
+    host = {k: vis.colormap.get_parameter(k) for k in ("vmin", "vmax", "log")}
+    assert dev["log"] == host["log"] is False
+    npt.assert_allclose([dev["vmin"], dev["vmax"]], [host["vmin"], host["vmax"]], rtol=1e-6, atol=1e-12)

@@ -46,7 +46,7 @@ class ContentStats(ctypes.Structure):
                 ("any_negative", ctypes.c_int32)]
 
 
-CONTENT_CH0, CONTENT_RATIO, CONTENT_ALL = 0, 1, 2
+CONTENT_CH0, CONTENT_RATIO, CONTENT_ALL, CONTENT_CH0_WHERE_CH1 = 0, 1, 2, 3
 
 
 class TsplatError(RuntimeError):

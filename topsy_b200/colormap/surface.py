@@ -73,9 +73,9 @@ class ColorAsSurfaceMap(Colormap):
         self._autorange_using_values(vals[..., 0].ravel()[valid])
 
     def autorange_device(self, image: torch.Tensor, mass_scale: float):
-        # the surface image holds maxima, not sums (no mass scale); "value where depth > 0" is not one of the device
-        # content kinds, and this runs only when the quantity or the mode changes, so the image is read back
-        self.autorange_vmin_vmax(image.cpu().numpy())
+        """Same decisions as ``autorange_vmin_vmax`` without the read-back.  The surface image holds maxima, not sums, so
+        there is no mass scale."""
+        self._autorange_device_values(image, N.CONTENT_CH0_WHERE_CH1, 1.0)
 
     def _update_parameter_buffer(self, width, height, mass_scale):
         p = self._surface_params

@@ -1379,7 +1379,7 @@ __global__ void __launch_bounds__(256) k_periodic_accumulate(const PeriodicArgs 
 // (colormap/implementation.py:381-425, :512-531, :576-588): min/max/sign statistics in one pass, then exact order
 // statistics by a 3-pass (11 + 11 + 10 bit) radix select over the monotone integer image of the float values.
 // ------------------------------------------------------------------------------------------------------------
-enum { CONTENT_CH0 = 0, CONTENT_RATIO = 1, CONTENT_ALL = 2 };
+enum { CONTENT_CH0 = 0, CONTENT_RATIO = 1, CONTENT_ALL = 2, CONTENT_CH0_WHERE_CH1 = 3 };
 
 struct ContentArgs {
     const float *image;
@@ -1394,6 +1394,8 @@ __device__ __forceinline__ float content_value(const ContentArgs &a, int64_t i)
     if (a.content == CONTENT_ALL) return a.image[i] * a.scale;
     const float c0 = a.image[i * a.channels] * a.scale;
     if (a.content == CONTENT_CH0) return c0;
+    if (a.content == CONTENT_CH0_WHERE_CH1)        // surface maps: the material value of the pixels that received a fragment
+        return a.image[i * a.channels + 1] > 0.0f ? c0 : __int_as_float(0x7fc00000);
     return (a.image[i * a.channels + 1] * a.scale) / c0;
 }
 
@@ -2002,8 +2004,9 @@ static int content_args(tsplat_ctx *c, const float *image, int res, int channels
     if (!c || !image) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
     if (channels != 1 && channels != 2 && channels != 4) return set_err(TSPLAT_ERR_INVALID, "channels must be 1, 2 or 4");
     if (res <= 0) return set_err(TSPLAT_ERR_INVALID, "bad resolution");
-    if (content < CONTENT_CH0 || content > CONTENT_ALL) return set_err(TSPLAT_ERR_INVALID, "bad content kind");
-    if (content == CONTENT_RATIO && channels < 2) return set_err(TSPLAT_ERR_INVALID, "ratio needs two channels");
+    if (content < CONTENT_CH0 || content > CONTENT_CH0_WHERE_CH1) return set_err(TSPLAT_ERR_INVALID, "bad content kind");
+    if ((content == CONTENT_RATIO || content == CONTENT_CH0_WHERE_CH1) && channels < 2)
+        return set_err(TSPLAT_ERR_INVALID, "this content kind needs two channels");
     a->image = image; a->channels = channels; a->content = content; a->scale = scale; a->use_log = 0;
     a->n_values = (int64_t)res * res * (content == CONTENT_ALL ? channels : 1);
     return TSPLAT_OK;
