@@ -91,6 +91,9 @@ class VisualizerCanvasBase:
             turn = np.array2string(vis.rotation_matrix, separator=",")
             print(f".translate({shift}).transform(np.array({turn}))")
 
+    def resize(self, *args):
+        """Window-system resize hook of the reference (canvas/__init__.py:96-98); there is no window here."""
+
     def resize_complete(self, width, height, pixel_ratio=1):
         self.pixel_ratio = pixel_ratio
         self.width_physical, self.height_physical = int(width * pixel_ratio), int(height * pixel_ratio)

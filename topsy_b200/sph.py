@@ -203,6 +203,14 @@ class DepthSPH(SPH):
         return N.MODE_DEPTH
 
 
+class LocalSphereKernel:
+    """Depth of a sphere of radius 2h below its silhouette, -0.01 outside it (sph.py:446-455); tabulated for the device by
+    ``kernel_lut.local_sphere_lut``."""
+
+    def get_value(self, distance):
+        return np.sqrt(4.0 - distance ** 2) if distance < 2.0 else -0.01
+
+
 class DepthSPHWithOcclusion(SPH):
     """Renders the front-most particles above a density cut: per pixel (quantity, depth) of the fragment nearest to the
     camera (reference: sph.py:457-601; vertex_depth_with_cut / fragment_raw, sph.wgsl:93-158).  The reference's depth

@@ -328,6 +328,20 @@ class VisualizerBase:
     def get_depth_image(self) -> np.ndarray:
         return self._sph.get_depth_image()
 
+    def sph_clipspace_to_screen_clipspace_matrix(self):
+        """Scaling that fits the square SPH image over the larger window dimension (visualizer.py:407-422); the colormap
+        and surface kernels apply the same mapping through ``window_aspect_ratio``."""
+        aspect_ratio = self.canvas.width_physical / self.canvas.height_physical
+        matr = np.eye(4, dtype=np.float32)
+        matr[0, 0] = 1.0 if aspect_ratio >= 1 else 1.0 / aspect_ratio
+        matr[1, 1] = aspect_ratio if aspect_ratio > 1 else 1.0
+        return matr
+
+    def show(self, force=False):
+        """The reference opens the Qt / Jupyter window here (visualizer.py:572-591).  Windowing is outside the B200 hot path:
+        the offscreen canvas is returned so that ``vis.show()`` in a script keeps working."""
+        return self.canvas
+
     def get_presentation_image(self, resolution=(640, 480)) -> np.ndarray:
         """What the window would show at ``resolution`` (without the matplotlib decorations of the reference)."""
         texture = self.device.create_texture((resolution[0], resolution[1], 1), self.canvas_format, label="output_texture")
