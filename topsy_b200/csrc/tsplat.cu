@@ -867,7 +867,7 @@ __device__ __forceinline__ void gather_accumulate(float (&acc)[8][ModeTraits<MOD
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
+__global__ void __launch_bounds__(256, GATHER_CTAS_PER_SM) k_tile_gather(const GatherArgs a)
 {
     constexpr int C = ModeTraits<MODE>::C;
     extern __shared__ __align__(16) unsigned char g_smem_raw[];
@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(256) k_tile_gather(const GatherArgs a)
         }
     }
     const unsigned lut_sa = (unsigned)__cvta_generic_to_shared(S.lut);      // < 64 KB: row addresses fit 16 bits
+    if (lut_sa + 260u * 64u >= 0x8000u) __trap();     // level-0 row addresses carry flags in bits 15 / 31 (never fires: lut is first)
     const int lx = (warp & 3) * 16 + (lane & 15);         // pixel column inside the tile
     const int ly0 = (warp >> 2) * 16 + (lane >> 4) * 8;   // first of the lane's 8 rows inside the tile
     const unsigned half4 = (unsigned)(lane >> 4) * 4u;    // which copy of an interleaved texel this half-warp reads
