@@ -87,3 +87,32 @@ def test_local_sphere_lut_shape_and_values():
     assert lut.shape == (o.LUT_TOTAL,) and lut.dtype == np.float32
     lvl3 = lut[o.LUT_LEVEL_OFFSETS[3]:].reshape(8, 8)
     assert lvl3[0, 0] == np.float32(-0.01) and lvl3[3, 3] == np.float32(np.sqrt(4 - 2 * 0.25 ** 2))
+
+
+@pytest.mark.parametrize("clamp_depth", [True, False])
+@pytest.mark.parametrize("scale", [30.0, 4.0])
+def test_numpy_and_c_surface_restatements_agree(clamp_depth, scale):
+    """Bit for bit, including a zoomed view where depths exceed 1.0 (where the two depth rules differ from each other)."""
+    fx = o.GMMFixture(1500)
+    ps = fx.pos_smooth()
+    q = fx.quantity.astype(np.float32)
+    cut = np.float32(o.density_cut_value(o.density_cut_table(fx.mass, fx.smooth), 30.0))
+    lut = o.local_sphere_lut()
+    M = o.transform_matrix(o.rotate(np.eye(3), 0.2, 0.7), np.zeros(3), scale); sf = o.scale_factor(scale)
+    a = o.splat_surface(ps[:, 0], ps[:, 1], ps[:, 2], ps[:, 3], fx.mass, q, M, sf, 96, lut, cut, clamp_depth=clamp_depth)
+    b = co.splat_surface(ps[:, 0], ps[:, 1], ps[:, 2], ps[:, 3], fx.mass, q, M, sf, 96, lut, cut, clamp_depth=clamp_depth)
+    assert (b[..., 1] > 0).mean() > 0.1
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_depth_rules_differ_only_beyond_unit_depth():
+    fx = o.GMMFixture(1500)
+    ps = fx.pos_smooth(); q = fx.quantity.astype(np.float32)
+    lut = o.local_sphere_lut()
+    M = o.transform_matrix(np.eye(3), np.zeros(3), 4.0); sf = o.scale_factor(4.0)
+    ref = co.splat_surface(ps[:, 0], ps[:, 1], ps[:, 2], ps[:, 3], fx.mass, q, M, sf, 96, lut, 0.0, clamp_depth=True)
+    mx = co.splat_surface(ps[:, 0], ps[:, 1], ps[:, 2], ps[:, 3], fx.mass, q, M, sf, 96, lut, 0.0, clamp_depth=False)
+    differ = (ref != mx).any(axis=2)
+    assert differ.any()                                   # the zoomed view does push fragments beyond depth 1
+    assert (mx[..., 1][differ] > 1.0).all()               # ... and only those pixels differ
+    assert (mx[..., 1] >= ref[..., 1]).all()
