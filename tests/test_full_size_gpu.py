@@ -1,5 +1,5 @@
 """Parity at BASELINE.json's FULL sizes (c2: 10M @ 1024^2 density, c3: 50M @ 2048^2 two-channel in EXPORT blocks,
-c4: 100M @ 2048^2 RGB) -- the synthetic workloads bench.py times.
+c4: 100M @ 2048^2 RGB, c5: one GPU's 125M share @ 4096^2 density) -- the synthetic workloads bench.py times.
 
 Two kinds of checks:
   * the whole image against the C/OpenMP oracle (fp64 accumulators; it finishes each workload in seconds on the box's
@@ -44,7 +44,7 @@ def _blocks(n, block=2 ** 25):
     return starts, np.minimum(block, n - starts)
 
 
-@pytest.mark.parametrize("name", ["c2", "c3", "c4"])
+@pytest.mark.parametrize("name", ["c2", "c3", "c4", "c5"])
 def test_full_size_workload_against_oracle(name, oracle_lut):
     wl, data, names, M, sf, eng = _setup(name)
     try:
