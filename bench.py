@@ -9,7 +9,7 @@ on the device.  Prints ONE JSON line (see the repository's DESIGN.md section 7 f
 
 `--impl reference`: the reference's GPU implementation (wgpu) and pynbody's CPU renderer cannot be installed in this
 image (no wheels, no network), so the reference arm times the CPU restatement of the same path (oracle/splat_oracle.c,
-fp32 accumulators, all host cores) on a bounded sample of the same workload -- kind "port".
+fp32 accumulators, all host cores) on the same workload at its full per-GPU size -- kind "port".
 """
 from __future__ import annotations
 
@@ -140,9 +140,38 @@ def camera_for(workload):
 
 MODE_ID = {"density": 0, "weighted": 1, "rgb": 2}
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_project_splat, one launch = 2^25 particles),
-# from the committed ncu capture; None where no capture exists for the workload
-NCU_TRAFFIC_PER_LAUNCH = {"c4": 1.055e9}
+
+def tracked_json(name):
+    """Numbers that come from committed profiler artefacts are READ from them at run time (profiles/r02/*.json)."""
+    p = ROOT / "profiles" / "r02" / name
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return {}
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and so its pinned staging buffers, by first touch) to the host NUMA node of its GPU.
+    Returns a short description for the JSON line.  No-op where sysfs has no NUMA information (single-node VMs)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        node = int(Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node").read_text())
+        if node < 0:
+            return "numa_node=-1 (not exposed)"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node}, {len(cpus)} cpus"
+        return f"numa node {node} has no allowed cpus"
+    except Exception as e:
+        return f"unavailable ({type(e).__name__})"
 
 
 def export_blocks(n, block=2 ** 25):
@@ -156,75 +185,115 @@ def footprint_stats(h, workload):
     return {"median_px": float(qs[0]), "p99_px": float(qs[1])}
 
 
+def host_threads():
+    # every host thread this process may use, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return ""
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(workload, host, n_sample, repeats=1):
-    """Times oracle/splat_oracle.c (fp32 accumulators, all cores) on the first n_sample particles."""
-    from oracle import c_oracle as co
-    from oracle import topsy_oracle as o
-    from topsy_b200 import synthetic
-    M, sf = camera_for(workload)
-    lut = o.kernel_lut()
-    names = synthetic.weight_names(workload.mode)
-    arrs = [host[k][:n_sample] for k in ("x", "y", "z", "h")]
-    w = [host[k][:n_sample] for k in names]
-    mode = MODE_ID[workload.mode]
-    R = workload.resolution
-    img = np.zeros((R, R, co.MODE_CHANNELS[mode]), np.float32)
-    # every host thread this process may use, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
-    try:
-        nthreads = len(os.sched_getaffinity(0))
-    except AttributeError:
-        nthreads = os.cpu_count() or 1
-    best = None
-    for _ in range(repeats):
+class CpuPort:
+    """oracle/splat_oracle.c (fp32 accumulators, thread-private images kept between calls) on host arrays."""
+
+    def __init__(self, workload, host):
+        from oracle import c_oracle as co
+        from oracle import topsy_oracle as o
+        from topsy_b200 import synthetic
+        self.co = co
+        self.M, self.sf = camera_for(workload)
+        self.lut = o.kernel_lut()
+        self.wl = workload
+        self.host = host
+        self.names = synthetic.weight_names(workload.mode)
+        self.mode = MODE_ID[workload.mode]
+        self.img = np.zeros((workload.resolution, workload.resolution, co.MODE_CHANNELS[self.mode]), np.float32)
+
+    def step(self, n_sample, nthreads):
+        h = self.host
+        arrs = [h[k][:n_sample] for k in ("x", "y", "z", "h")]
+        w = [h[k][:n_sample] for k in self.names]
         t0 = time.perf_counter()
-        co.splat(*arrs, w, M, sf, R, mode, lut, out=img, clear=True, accum=np.float32, nthreads=nthreads)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
+        self.co.splat(*arrs, w, self.M, self.sf, self.wl.resolution, self.mode, self.lut, out=self.img, clear=True,
+                      accum=np.float32, nthreads=nthreads)
+        return time.perf_counter() - t0
+
+
+def cpu_port_rate(workload, host, n_sample, repeats=1, nthreads=None):
+    """Best-of-`repeats` rate of the CPU port on the first n_sample particles: (Gparticles/s, seconds, threads)."""
+    port = CpuPort(workload, host)
+    nthreads = host_threads() if nthreads is None else nthreads
+    best = min(port.step(n_sample, nthreads) for _ in range(repeats))
     return n_sample / best / 1e9, best, nthreads
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the path on the box's host cores, on THIS arm's workload.
+
+    Each step splats the whole per-GPU particle set of the workload (c4: 100 M) into the full-resolution image -- the same
+    configuration as our arm at N = 1 -- unless that would make `--steps + --warmup` steps take longer than ~4 minutes,
+    in which case a step is the first n_sample >= 32 M particles (size printed; no extrapolation: the value is
+    n_sample / time).  The thread-private images are allocated once and reused (oracle/splat_oracle.c workspace)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     from topsy_b200 import synthetic
     wl = synthetic.WORKLOADS[args.workload]
-    n_total = wl.n_particles * args.gpus
-    # bounded sample: calibrate on 2e5 particles, then size each step to ~3 s of CPU work
+    n_full = wl.n_particles if args.particles is None else args.particles
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    n_gen = min(wl.n_particles if args.particles is None else args.particles, 20_000_000)
-    data = synthetic.generate(wl, dev, n_total=wl.n_particles if args.particles is None else args.particles, n=n_gen)
+    data, _ = synthetic.generate_striped(wl, dev, n_total=n_full, h_count=n_full)
     host = {k: v.cpu().numpy() for k, v in data.items()}
     del data
-    rate0, _, cores = cpu_port_rate(wl, host, min(200_000, n_gen))
-    n_sample = int(min(n_gen, max(200_000, rate0 * 1e9 * 3.0)))
+    cores = host_threads()
+    port = CpuPort(wl, host)
+    n_cal = min(n_full, 16_000_000)
+    port.step(n_cal, cores)                                   # touches the workspace
+    t_cal = port.step(n_cal, cores)
+    est_full = t_cal * n_full / n_cal
+    budget_s = 240.0
+    n_steps_all = max(args.steps + args.warmup, 1)
+    if est_full * n_steps_all <= budget_s:
+        n_sample = n_full
+    else:
+        n_sample = int(min(n_full, max(32_000_000, n_cal * budget_s / n_steps_all / t_cal)))
     for _ in range(args.warmup):
-        cpu_port_rate(wl, host, n_sample)
+        port.step(n_sample, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_rate(wl, host, n_sample)
+        port.step(n_sample, cores)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = n_sample / dt / 1e9
-    cpu_name = ""
-    try:
-        for ln in open("/proc/cpuinfo"):
-            if ln.startswith("model name"):
-                cpu_name = ln.split(":", 1)[1].strip(); break
-    except Exception:
-        pass
-    sample = f"first {n_sample} particles of workload {wl.name} ({wl.description}) per step, full {wl.resolution}^2 image"
+    # single-thread figure (BASELINE.md section 3), on a bounded sample, outside the timed steps
+    n_one = min(n_full, 4_000_000)
+    t_one = port.step(n_one, 1)
+    same = n_sample == n_full
+    sample = (f"all {n_sample} particles of workload {wl.name} ({wl.description}) per step" if same else
+              f"first {n_sample} of the {n_full} particles of workload {wl.name} ({wl.description}) per step") + \
+             f", full {wl.resolution}^2 image, particles in cell order (the order topsy keeps them in)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl.name}: {wl.description}", "resolution": wl.resolution, "mode": wl.mode,
-                       "particles_per_step": n_sample, "note": "wgpu/pynbody not installable here: CPU restatement "
-                       "(oracle/splat_oracle.c, OpenMP, fp32 accumulators) of the reference path"},
+                       "particles_per_step": n_sample, "particles_per_gpu": n_full, "same_config_as_gpu_arm": same,
+                       "note": "wgpu/pynbody not installable here: CPU restatement (oracle/splat_oracle.c, OpenMP, fp32 "
+                               "accumulators, thread-private images reused between steps) of the reference path"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "cpu": cpu_name, "os_cpu_count": os.cpu_count()},
+                             "cpu": cpu_model(), "os_cpu_count": os.cpu_count(),
+                             "single_thread": {"value": n_one / t_one / 1e9, "unit": UNIT, "sample": f"first {n_one} particles, 1 thread"}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -232,12 +301,40 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
+def colormap_params_for(wl, dev):
+    """Colormap stage: rgb -> tri-band log/gamma map; density/weighted -> log10 + 1-D LUT (colormap/implementation.py)."""
+    import torch
+    from topsy_b200 import _native as N
+    from topsy_b200.colormap import luts
+    params = N.ColormapParams()
+    params.window_aspect_ratio = 1.0; params.gamma = 1.0; params.log_scale = 1
+    params.density_vmin = 0.0; params.density_vmax = 1.0
+    if wl.mode == "rgb":
+        params.kind = N.CMAP_RGB; lut = None
+    else:
+        params.kind = N.CMAP_WEIGHTED if wl.mode == "weighted" else N.CMAP_DENSITY
+        lut = torch.from_numpy(luts.colormap_table_1d("twilight_shifted", 1000)).to(dev)
+    return params, lut
+
+
+def rel_err(got, ref):
+    """max over channels of the per-pixel relative error where the reference pixel exceeds 1e-6 of the channel maximum
+    (the north_star tolerance definition)."""
+    import torch
+    worst = 0.0
+    for c in range(ref.shape[2]):
+        r = ref[..., c].double(); g = got[..., c].double()
+        big = r.abs() > 1e-6 * r.abs().max()
+        if bool(big.any()):
+            worst = max(worst, float(((g[big] - r[big]).abs() / r[big].abs()).max()))
+    return worst
+
+
 def run_ours(args):
+    import datetime
     import torch
     import torch.distributed as dist
     from topsy_b200 import synthetic, _native as N
-    from topsy_b200.engine import SplatEngine
-    from topsy_b200.colormap import luts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,17 +343,21 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: first touch places the staging buffers
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=30))
 
     wl = synthetic.WORKLOADS[args.workload]
-    n = wl.n_particles if args.particles is None else args.particles
-    n_total = n * world
+    n_per_gpu = wl.n_particles if args.particles is None else args.particles
+    n_total = n_per_gpu * world
     R = wl.resolution
     mode = MODE_ID[wl.mode]
     C = N.MODE_CHANNELS[mode]
-    data = synthetic.generate(wl, dev, n_total=n, rank=rank, n=n)     # footprints fixed per GPU: weak scaling keeps per-GPU work constant
+    # ONE snapshot of n_total particles in topsy's cell order; this rank holds its per-cell stripe.  Smoothing lengths are
+    # set from the per-GPU count so that weak scaling keeps the per-GPU footprint (and so the per-GPU work) fixed.
+    data, cell_lengths = synthetic.generate_striped(wl, dev, n_total=n_total, rank=rank, world=world, h_count=n_per_gpu)
+    n = int(data["x"].numel())
     names = synthetic.weight_names(wl.mode)
     M, sf = camera_for(wl)
 
@@ -267,18 +368,8 @@ def run_ours(args):
     eng.set_particles(data["x"], data["y"], data["z"], data["h"])
     eng.set_weights(*[data[k] for k in names])
     blocks = export_blocks(n)
-    img = sharded.image
     out = sharded.out
-
-    # colormap stage: rgb -> tri-band log/gamma map; density/weighted -> log10 + 1-D LUT (implementation.py)
-    params = N.ColormapParams()
-    params.window_aspect_ratio = 1.0; params.gamma = 1.0; params.log_scale = 1
-    params.density_vmin = 0.0; params.density_vmax = 1.0
-    if wl.mode == "rgb":
-        params.kind = N.CMAP_RGB; lut = None
-    else:
-        params.kind = N.CMAP_WEIGHTED if wl.mode == "weighted" else N.CMAP_DENSITY
-        lut = torch.from_numpy(luts.colormap_table_1d("twilight_shifted", 1000)).to(dev)
+    params, lut = colormap_params_for(wl, dev)
 
     def frame(ev=None):
         sharded.splat(mode, blocks)
@@ -295,13 +386,54 @@ def run_ours(args):
     ch = full[..., :3] if wl.mode == "rgb" else (full[..., 1] / full[..., 0] if wl.mode == "weighted" else full[..., 0])
     v = torch.log10(ch[ch > 0].flatten().float())
     if v.numel() > 200:
-        sub = v[torch.randint(0, v.numel(), (min(v.numel(), 2_000_000),), device=dev)]
+        g = torch.Generator(device=dev); g.manual_seed(1)
+        sub = v[torch.randint(0, v.numel(), (min(v.numel(), 2_000_000),), device=dev, generator=g)]
         vmax = float(torch.quantile(sub, 0.999)); vmin = float(torch.quantile(sub, 0.01))
         if wl.mode == "rgb":
             vmin = vmax - 3.0
     else:
         vmin, vmax = 0.0, 1.0
+    if world > 1:                                  # identical parameters on every rank
+        vv = torch.tensor([vmin, vmax], device=dev, dtype=torch.float64)
+        dist.broadcast(vv, 0)
+        vmin, vmax = float(vv[0]), float(vv[1])
     params.vmin, params.vmax = vmin, vmax
+
+    # ---- N > 1: parity of the sharded frame with a single-GPU render of the SAME snapshot (outside the timed region) ----
+    parity = None
+    if world > 1:
+        frame()
+        torch.cuda.synchronize()
+        got = sharded.reduced_image()              # all-reduce of the partial images: the sum the fused kernel colormaps
+        if rank == 0:
+            from topsy_b200.engine import SplatEngine
+            ref_eng = SplatEngine(R, device=local_rank)
+            ref_eng.set_camera(M, sf)
+            ref_img = torch.zeros((R, R, C), dtype=torch.float32, device=dev)
+            for g_ in range(world):                # rank 0 walks all stripes of the snapshot, one after the other
+                d2, _ = synthetic.generate_striped(wl, dev, n_total=n_total, rank=g_, world=world, h_count=n_per_gpu)
+                ref_eng.set_particles(d2["x"], d2["y"], d2["z"], d2["h"])
+                ref_eng.set_weights(*[d2[k] for k in names])
+                for i, (s_, l_) in enumerate(export_blocks(int(d2["x"].numel()))):
+                    ref_eng.render(mode, [s_], [l_], clear=(g_ == 0 and i == 0), image=ref_img)
+                torch.cuda.synchronize()
+                del d2
+            err = rel_err(got, ref_img)
+            # the RGBA image the fused reduce+colormap kernel left on rank 0 against the colormap of the single-GPU image
+            want = torch.empty_like(out)
+            ref_eng.colormap(ref_img, params, lut, want, sharded._fmt)
+            torch.cuda.synchronize()
+            dpx = (out.to(torch.int32) - want.to(torch.int32)).abs() if out.dtype == torch.uint8 else (out.float() - want.float()).abs()
+            parity = {"max_rel_err": err, "tolerance": 1e-4, "ok": bool(err <= 1e-4),
+                      "rgba_max_abs_diff": float(dpx.max()), "rgba_frac_differing": float((dpx > 0).float().mean()),
+                      "what": f"sum of the {world} per-rank partial images vs ONE GPU splatting all {n_total} particles of the same "
+                              "snapshot (all stripes, in sequence); pixels above 1e-6 of the channel maximum; and the RGBA output "
+                              "of the fused reduce+colormap kernel vs tsplat_colormap of the single-GPU image"}
+            del ref_img, want
+            ref_eng.close()
+        del got
+        torch.cuda.empty_cache()
+        dist.barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -339,6 +471,27 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = n_total / (ms_per_step * 1e-3) / 1e9
 
+    # ---- the same particles with sub-pixel footprints (h x 0.3): the regime where the HBM roofline is the binding one ----
+    subpixel = None
+    if wl.name == "c4" and world == 1:
+        h_small = data["h"] * 0.3
+        eng.set_particles(data["x"], data["y"], data["z"], h_small)
+        eng.set_weights(*[data[k] for k in names])
+        for _ in range(3):
+            sharded.splat(mode, blocks)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            sharded.splat(mode, blocks)
+        e1.record()
+        torch.cuda.synchronize()
+        sub_ms = e0.elapsed_time(e1) / args.steps
+        subpixel = {"splat_ms": sub_ms, "footprint_px": footprint_stats(h_small[: min(n, 2_000_000)].cpu().numpy(), wl)}
+        eng.set_particles(data["x"], data["y"], data["z"], data["h"])
+        eng.set_weights(*[data[k] for k in names])
+        del h_small
+
     # ---- end-to-end: host buffers in, RGBA image out, copies inside the timed region -------------------------
     e2e = None
     if not args.no_e2e:
@@ -346,49 +499,59 @@ def run_ours(args):
         host = {k: torch.empty(n, dtype=torch.float32, pin_memory=True) for k in keys}
         for k in keys:
             host[k].copy_(data[k])
-        host_out = torch.empty((R, R, 4), dtype=torch.uint8, pin_memory=True)
+        host_out = [torch.empty((R, R, 4), dtype=out.dtype, pin_memory=True) for _ in range(2)]
         torch.cuda.synchronize()
         h2d = sum(host[k].numel() * 4 for k in keys)
-        d2h = host_out.numel()
+        d2h = host_out[0].numel() * host_out[0].element_size()
 
         copy_stream = torch.cuda.Stream(device=dev)
+        h2d_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
-        def e2e_frame():
+        def e2e_frame(i, timed=False):
             # the uploads of EXPORT block b+1 overlap the splat of block b: copies on their own stream, one event per block
             main = torch.cuda.current_stream(dev)
             copy_stream.wait_stream(main)                 # the previous frame has finished reading the device arrays
             ready = []
             with torch.cuda.stream(copy_stream):
+                if timed:
+                    h2d_ev[0].record(copy_stream)
                 for (s, l) in blocks:
                     for k in keys:
                         eng.upload(data[k][s:s + l], host[k][s:s + l])
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
                     ready.append(ev)
-            for i, (s, l) in enumerate(blocks):
-                main.wait_event(ready[i])
-                eng.render(mode, [s], [l], clear=(i == 0), image=sharded.image)
+                if timed:
+                    h2d_ev[1].record(copy_stream)
+            for b, (s, l) in enumerate(blocks):
+                main.wait_event(ready[b])
+                eng.render(mode, [s], [l], clear=(b == 0), image=sharded.image)
             sharded.present(params, lut)
-            eng.download(host_out, out)
+            if rank == 0:
+                eng.download(host_out[i & 1], out)
             eng.synchronize()
 
         n_e2e = max(2, min(args.steps, 5))
-        e2e_frame()
+        e2e_frame(0)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_frame()
+        for i in range(n_e2e):
+            e2e_frame(i, timed=(i == n_e2e - 1))
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / n_e2e
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        h2d_gbs = h2d / (h2d_ev[0].elapsed_time(h2d_ev[1]) * 1e-3) / 1e9
+        tt = torch.tensor([dt, -h2d_gbs], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
-        e2e = {"value": n_total / dt / 1e9, "unit": UNIT, "ms_per_frame": dt * 1e3, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "frames": n_e2e,
-               "path": "pinned host SoA -> tsplat_memcpy_h2d per EXPORT block on a copy stream, overlapped with tsplat_render of the previous block -> tsplat_colormap -> tsplat_memcpy_d2h"}
+        e2e = {"value": n_total / dt / 1e9, "unit": UNIT, "ms_per_frame": dt * 1e3, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h, "frames": n_e2e, "h2d_GBs_per_gpu_min_over_ranks": -float(tt[1]),
+               "host_binding": numa,
+               "path": "pinned host SoA (allocated after binding the rank to its GPU's NUMA node) -> tsplat_memcpy_h2d per EXPORT "
+                       "block on a copy stream, overlapped with tsplat_render of the previous block -> [image sum +] "
+                       "tsplat_colormap -> tsplat_memcpy_d2h on rank 0"}
         del host
 
     if rank == 0:
@@ -396,52 +559,65 @@ def run_ours(args):
         bytes_alg = n * wl.bytes_per_particle          # per GPU, per frame: compulsory particle reads of the splat pass
         achieved = bytes_alg / (splat_ms_max * 1e-3) / 1e9
         h_cpu = data["h"][: min(n, 2_000_000)].cpu().numpy()
+        traffic = tracked_json("ncu_traffic.json").get(wl.name, {})
+        red = tracked_json("red_peaks.json")
+        red_peak = red.get("quad_pattern_lanes_per_s")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl.name}: {wl.description}", "particles_per_gpu": n, "particles_total": n_total,
                        "resolution": R, "mode": wl.mode, "channels": C, "scale": wl.scale, "rotate": list(wl.rotate),
-                       "generator": "uniform box, lognormal h (topsy_b200/synthetic.py)", "h_factor": wl.h_factor,
+                       "generator": "one uniform-box snapshot of particles_total particles in topsy's cell order (16^3 cells, shuffled "
+                                    "inside cells), lognormal h; each rank holds its per-cell stripe (topsy_b200/synthetic.py generate_striped)",
+                       "h_factor": wl.h_factor,
                        "footprint_px": footprint_stats(h_cpu, wl), "blocks_per_frame": len(blocks),
                        "l2_policy": "inputs (%.2f GB per frame) exceed the 126 MB L2; no flush needed" % (bytes_alg / 1e9),
-                       "parallelism": (f"particle shards x{world}; image sum = {sharded.method} "
+                       "parallelism": (f"particle stripes x{world}; image sum = {sharded.method} "
                                        f"({'fused reduce+colormap kernel over NVLink peer memory' if sharded.method == 'p2p' else 'NCCL reduce + colormap'})")
                        if world > 1 else "single GPU"},
             "phases_ms": {"splat": splat_ms_max, "reduce_and_colormap": present_ms},
-            "roofline": {"bound": "hbm", "kernel": "k_project_splat (+ deferred queue kernels) per frame",
+            "roofline": {"bound": "hbm", "kernel": "k_project_stream (+ deferred queue kernels) per frame",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "frac_of_nominal_8000_GBs": achieved / 8000.0,
                          "algorithmic_bytes_per_frame": bytes_alg,
                          "algorithmic_bytes_per_launch": min(n, 2 ** 25) * wl.bytes_per_particle,
-                         "traffic": NCU_TRAFFIC_PER_LAUNCH.get(wl.name),
-                         "traffic_source": "profiles/r01/k1_c4_dram_traffic_v5.txt (ncu dram__bytes_read+write per 2^25-particle launch)"
-                         if wl.name in NCU_TRAFFIC_PER_LAUNCH else None,
+                         "traffic": traffic.get("dram_bytes_per_launch"),
+                         "traffic_source": traffic.get("source"),
                          "bytes_per_particle": wl.bytes_per_particle},
-            "atomic_roofline": {"bound": "vector RED lane rate of the SM's LSU/L1TEX pipe, measured for lanes grouped in 2x2 pixel "
-                                         "quads like this workload's footprints (profiles/r01/red_patterns_b200.txt: 2.38e11 lanes/s; "
-                                         "1.84e11 fully scattered, 3.5e11 fully coalesced rows)",
-                                "direct_vector_reds_per_frame": int(st["direct_vector_reds"]),
-                                "achieved": st["direct_vector_reds"] / (splat_ms_max * 1e-3), "peak": 2.38e11, "unit": "RED lanes/s",
-                                "frac": st["direct_vector_reds"] / (splat_ms_max * 1e-3) / 2.38e11,
-                                "reds_per_particle": st["direct_vector_reds"] / max(n, 1)},
             "gpu_launches": int(launches),
             "stats": {k: int(v) for k, v in st.items()},
             "wall_ms_per_step": t_wall * 1e3 / args.steps,
             "clocks": clocks,
         }
+        if red_peak:
+            lanes = st["direct_vector_reds"] / max(args.steps + args.warmup + (2 if world > 1 else 1), 1)
+            line["atomic_roofline"] = {
+                "bound": "vector RED lane rate for lanes grouped in 2x2 pixel quads like this workload's footprints, read from "
+                         "profiles/r02/red_peaks.json (measured on B200 by profiles/microbench/red_patterns_bench.cu and "
+                         "red_layout_bench.cu; chip-wide L2 limit, not per-SM)",
+                "direct_vector_reds_per_frame": int(lanes), "achieved": lanes / (splat_ms_max * 1e-3), "peak": red_peak,
+                "unit": "RED lanes/s", "frac": lanes / (splat_ms_max * 1e-3) / red_peak, "reds_per_particle": lanes / max(n, 1)}
+        if subpixel is not None:
+            sub_ach = bytes_alg / (subpixel["splat_ms"] * 1e-3) / 1e9
+            line["roofline_subpixel"] = {"bound": "hbm", "what": "the same 100 M particles with h x 0.3 (sub-pixel footprints): the regime "
+                                         "in which the HBM roofline, not the RED rate, binds k_project_stream",
+                                         "splat_ms": subpixel["splat_ms"], "achieved": sub_ach, "peak": peak, "unit": "GB/s",
+                                         "frac": sub_ach / peak, "footprint_px": subpixel["footprint_px"],
+                                         "Gparticles_per_s": n / (subpixel["splat_ms"] * 1e-3) / 1e9}
+        if parity is not None:
+            line["parity"] = parity
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
-            n_c = min(n, 4_000_000)
+            n_c = min(n, 32_000_000)
             host_np = {k: data[k][:n_c].cpu().numpy() for k in ["x", "y", "z", "h"] + list(names)}
-            r0, _, cores = cpu_port_rate(wl, host_np, min(200_000, n_c))
-            n_s = int(min(n_c, max(200_000, r0 * 1e9 * 5.0)))
-            rate, secs, cores = cpu_port_rate(wl, host_np, n_s, repeats=3)
+            rate, secs, cores = cpu_port_rate(wl, host_np, n_c, repeats=3)
+            rate1, secs1, _ = cpu_port_rate(wl, host_np, min(n_c, 2_000_000), repeats=1, nthreads=1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {n_s} particles of the same workload, best of 3 ({secs:.2f} s each), "
-                                              f"oracle/splat_oracle.c with fp32 accumulators",
-                                    "os_cpu_count": os.cpu_count()}
+                                    "sample": f"first {n_c} particles of the same workload (cell order), best of 3 ({secs:.2f} s each), "
+                                              f"oracle/splat_oracle.c with fp32 accumulators, thread-private images reused",
+                                    "single_thread_value": rate1, "os_cpu_count": os.cpu_count(), "cpu": cpu_model()}
         if args.progressive and world == 1:
             del data
             sharded.close()
@@ -449,6 +625,7 @@ def run_ours(args):
             line["progressive"] = progressive_report(wl, n)
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

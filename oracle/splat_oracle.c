@@ -18,6 +18,9 @@
  *   oracle_splat_f64  : fp64 accumulators  -> the checker
  *   oracle_splat_f32  : fp32 accumulators  -> the timed CPU baseline (the reference blends in fp32)
  * Both use thread-private images followed by a parallel sum (the strategy BASELINE.md section 3 prescribes).
+ * The private images live in a workspace that is allocated once and reused by later calls (oracle_release_workspace()
+ * frees it): a call pays one parallel clear and one parallel sum of the T images, not T page-faulting allocations, so
+ * the timed CPU baseline does not depend on how few particles a step holds.
  */
 #include <math.h>
 #include <stdint.h>
@@ -26,6 +29,27 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+/* persistent thread-private accumulation images (one per OpenMP thread beyond thread 0, which uses the output) */
+#define ORACLE_MAX_THREADS 1024
+static void *g_priv[ORACLE_MAX_THREADS];
+static size_t g_priv_bytes[ORACLE_MAX_THREADS];
+
+static void *workspace_get(int t, size_t bytes)
+{
+    if (t < 0 || t >= ORACLE_MAX_THREADS) return NULL;
+    if (g_priv_bytes[t] < bytes) {
+        free(g_priv[t]);
+        g_priv[t] = malloc(bytes);          /* first touched (cleared) by the owning thread: NUMA-local pages */
+        g_priv_bytes[t] = g_priv[t] ? bytes : 0;
+    }
+    return g_priv[t];
+}
+
+void oracle_release_workspace(void)
+{
+    for (int t = 0; t < ORACLE_MAX_THREADS; ++t) { free(g_priv[t]); g_priv[t] = NULL; g_priv_bytes[t] = 0; }
+}
 
 enum { MODE_DENSITY = 0, MODE_WEIGHTED = 1, MODE_RGB = 2, MODE_DEPTH = 3 };
 static const int MODE_CHANNELS[4] = {1, 2, 4, 2};
@@ -139,15 +163,17 @@ int NAME(const float *x, const float *y, const float *z, const float *h,        
         nt = 1;                                                                                                \
         _Pragma("omp parallel") { _Pragma("omp single") nt = omp_get_num_threads(); }                         \
     }                                                                                                          \
+    if (nt > ORACLE_MAX_THREADS) nt = ORACLE_MAX_THREADS;                                                      \
     ACC_T **priv = (ACC_T **)calloc(nt, sizeof(ACC_T *));                                                      \
     if (!priv) return -3;                                                                                      \
     int fail = 0;                                                                                              \
     _Pragma("omp parallel num_threads(nt)")                                                                    \
     {                                                                                                          \
         int t = omp_get_thread_num();                                                                          \
-        ACC_T *mine = (t == 0) ? img : (ACC_T *)calloc(npx, sizeof(ACC_T));                                    \
+        ACC_T *mine = (t == 0) ? img : (ACC_T *)workspace_get(t, npx * sizeof(ACC_T));                         \
         priv[t] = mine;                                                                                        \
         if (!mine) { _Pragma("omp atomic write") fail = 1; }                                                   \
+        else if (t != 0) memset(mine, 0, npx * sizeof(ACC_T));                                                 \
         _Pragma("omp barrier")                                                                                 \
         if (!fail) {                                                                                           \
             for (int r = 0; r < nranges; ++r) {                                                                \
@@ -165,7 +191,6 @@ int NAME(const float *x, const float *y, const float *z, const float *h,        
                 img[q] = s;                                                                                    \
             }                                                                                                  \
         }                                                                                                      \
-        if (t != 0) free(mine);                                                                                \
     }                                                                                                          \
     free(priv);                                                                                                \
     return fail ? -3 : 0;                                                                                      \

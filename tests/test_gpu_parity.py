@@ -186,3 +186,51 @@ def test_pair_capacity_overflow_falls_back_to_atomics(oracle_lut):
         assert_image_parity(img, ref, "pair overflow")
     finally:
         eng.close()
+
+
+def test_oversize_range_in_multi_range_call_is_split(oracle_lut):
+    """a multi-range call in which ONE range exceeds the scratch queue capacity (a clustered
+    snapshot with one huge cell) used to fail with 'a single range exceeds the scratch capacity'; it must be split
+    like the single-range path does.  Scratch is sized for 2^20 particles per call, the first range holds 2.5 M."""
+    from topsy_b200.engine import SplatEngine
+    rs = np.random.RandomState(17)
+    n, R = 3_000_000, 256
+    pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+    h = (0.004 * np.exp(rs.normal(size=n) * 0.6)).astype(np.float32)        # ~0.5 px .. 3 px: direct + some deferred
+    h[::1000] *= 30.0                                                        # a few big footprints in every range
+    m = rs.uniform(0.5, 1.5, n).astype(np.float32)
+    M = o.transform_matrix(o.rotate(np.eye(3), 0.1, 0.2), np.zeros(3), 1.0); sf = o.scale_factor(1.0)
+    starts = np.array([3, 2_500_001, 2_800_000], np.int64)
+    lens = np.array([2_499_998, 250_000, 199_999], np.int64)
+    ref = co.splat(pos[:, 0], pos[:, 1], pos[:, 2], h, (m,), M, sf, R, o.MODE_DENSITY, oracle_lut, ranges=(starts, lens))
+    eng = SplatEngine(R, max_particles_per_call=1 << 20)
+    try:
+        eng.set_kernel_lut(oracle_lut)
+        eng.set_camera(M, sf)
+        x, y, z, hd, md = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], h, m)
+        eng.set_particles(x, y, z, hd); eng.set_weights(md)
+        img = eng.render(o.MODE_DENSITY, starts, lens).cpu().numpy()
+        assert eng.stats()["particles_submitted"] == lens.sum()
+        assert_image_parity(img, ref, "oversize range")
+    finally:
+        eng.close()
+
+
+def test_more_ranges_than_one_table_holds(engine200, oracle_lut):
+    """more than 65536 ranges in one call (ArrayDataLoader with nside >= 41) are processed in batches."""
+    rs = np.random.RandomState(23)
+    n = 70_000 * 3
+    pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+    h = (0.01 * np.exp(rs.normal(size=n) * 0.5)).astype(np.float32)
+    m = rs.uniform(0.5, 1.5, n).astype(np.float32)
+    M = o.transform_matrix(np.eye(3), np.zeros(3), 1.0); sf = o.scale_factor(1.0)
+    starts = np.arange(70_000, dtype=np.int64) * 3
+    lens = np.full(70_000, 2, np.int64)
+    ref = co.splat(pos[:, 0], pos[:, 1], pos[:, 2], h, (m,), M, sf, 200, o.MODE_DENSITY, oracle_lut, ranges=(starts, lens))
+    x, y, z, hd, md = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], h, m)
+    engine200.set_kernel_lut(oracle_lut)
+    engine200.set_camera(M, sf)
+    engine200.set_particles(x, y, z, hd); engine200.set_weights(md)
+    img = engine200.render(o.MODE_DENSITY, starts, lens).cpu().numpy()
+    assert engine200.stats()["particles_submitted"] == lens.sum()
+    assert_image_parity(img, ref, "70000 ranges")

@@ -23,7 +23,9 @@
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 #include <new>
+#include <algorithm>
 
 using namespace tsplat;
 
@@ -99,6 +101,7 @@ struct tsplat_ctx {
     int64_t scratch_bytes;
     Counters *d_counters;
     void *d_select;              // histograms / statistics of the device autorange (32 KB)
+    unsigned *h_select;          // pinned staging of the same size (per context: contexts may be used from different threads)
     // range staging
     int64_t *h_ranges[RANGE_SLOTS];
     int64_t *d_ranges[RANGE_SLOTS];
@@ -485,6 +488,8 @@ __global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs 
     }
 #endif
 }
+
+#include "tsplat_project.cuh"
 
 // ------------------------------------------------------------------------------------------------------------
 // K3b: cooperative atomic splat of queue records (one warp per record, lanes along pixel rows)
@@ -1508,6 +1513,7 @@ extern "C" int tsplat_create(int device_ordinal, int resolution, tsplat_ctx **ou
     CUDA_TRY(cudaMalloc(&c->d_counters, sizeof(Counters)));
     CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(Counters)));
     CUDA_TRY(cudaMalloc(&c->d_select, sizeof(unsigned) * 4 * 2048));
+    CUDA_TRY(cudaMallocHost(&c->h_select, sizeof(unsigned) * 4 * 2048));
     for (int s = 0; s < RANGE_SLOTS; ++s) {
         CUDA_TRY(cudaMallocHost(&c->h_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
         CUDA_TRY(cudaMalloc(&c->d_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
@@ -1526,6 +1532,7 @@ extern "C" int tsplat_destroy(tsplat_ctx *c)
     cudaFree(c->d_slut);
     cudaFree(c->d_counters);
     cudaFree(c->d_select);
+    cudaFreeHost(c->h_select);
     for (int s = 0; s < RANGE_SLOTS; ++s) {
         cudaFreeHost(c->h_ranges[s]);
         cudaFree(c->d_ranges[s]);
@@ -1662,8 +1669,22 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
     if (blocks > 0) {
         // cell width of the vector REDs: as many pixels as fit 128 bits, if rows keep the cells aligned
         constexpr int CW = ModeTraits<MODE>::C == 1 ? 4 : ModeTraits<MODE>::C == 2 ? 2 : 1;
-        if (CW > 1 && (c->R % CW) == 0) k_project_splat<MODE, CW><<<(unsigned)blocks, threads, 0, st>>>(pa);
-        else k_project_splat<MODE, 1><<<(unsigned)blocks, threads, 0, st>>>(pa);
+        static const bool use_v1 = getenv("TSPLAT_K1_V1") != nullptr;       // round-1 kernel, kept for A/B timing only
+        if (use_v1) {
+            if (CW > 1 && (c->R % CW) == 0) k_project_splat<MODE, CW><<<(unsigned)blocks, threads, 0, st>>>(pa);
+            else k_project_splat<MODE, 1><<<(unsigned)blocks, threads, 0, st>>>(pa);
+        } else {
+            // persistent warps: one batch of 128 particles per warp and iteration, KP_CTAS_PER_SM resident CTAs per SM
+            const int64_t n_batches = (n_groups + 31) >> 5;
+            int64_t grid = (n_batches + KP_WARPS - 1) / KP_WARPS;
+            if (CW > 1 && (c->R % CW) == 0) {
+                const int64_t max_grid = (int64_t)c->sm_count * kp_ctas_per_sm<MODE, CW>();
+                k_project_stream<MODE, CW><<<(unsigned)(grid < max_grid ? grid : max_grid), KP_THREADS, 0, st>>>(pa);
+            } else {
+                const int64_t max_grid = (int64_t)c->sm_count * kp_ctas_per_sm<MODE, 1>();
+                k_project_stream<MODE, 1><<<(unsigned)(grid < max_grid ? grid : max_grid), KP_THREADS, 0, st>>>(pa);
+            }
+        }
         c->launches++;
     }
     if (pa.queue_cap > 0 && pa.small_call) {
@@ -1760,7 +1781,7 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
     if ((mode == TSPLAT_MODE_WEIGHTED || mode == TSPLAT_MODE_RGB || mode == TSPLAT_MODE_SURFACE) && c->n > 0 && !c->w1)
         return set_err(TSPLAT_ERR_STATE, "second weight array not set");
     if (mode == TSPLAT_MODE_RGB && c->n > 0 && !c->w2) return set_err(TSPLAT_ERR_STATE, "third weight array not set");
-    if (n_ranges < 0 || n_ranges > MAX_RANGES) return set_err(TSPLAT_ERR_INVALID, "n_ranges %d out of [0, %d]", n_ranges, MAX_RANGES);
+    if (n_ranges < 0) return set_err(TSPLAT_ERR_INVALID, "n_ranges %d is negative", n_ranges);
     if (n_ranges > 0 && (!starts || !lens)) return set_err(TSPLAT_ERR_INVALID, "NULL range arrays");
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1827,29 +1848,33 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
             s = ce;
         }
     } else {
-        // multi-range: stage (start, end, gprefix) through a pinned ring slot; chunk by cumulative particle count
+        // multi-range: stage (start, end, gprefix) through a pinned ring slot; chunk by cumulative particle count.
+        // A launch takes at most chunk_cap particles and MAX_RANGES ranges; a range longer than what is left of the
+        // chunk is split (cursor = range r0, offset off0 into it), so neither a huge cell nor more than MAX_RANGES cells
+        // per call is an error.
         int r0 = 0;
+        int64_t off0 = 0;
         while (r0 < n_ranges) {
             const int slot = c->range_slot;
             c->range_slot = (c->range_slot + 1) % RANGE_SLOTS;
             CUDA_TRY(cudaEventSynchronize(c->range_evt[slot]));     // previous use of this slot has been copied
             int64_t *hs = c->h_ranges[slot];
             int64_t acc = 0, groups = 0;
-            int r1 = r0, m = 0;
-            // layout: start[m] | end[m] | gprefix[m+1]  (m known only at the end -> use MAX stride of this chunk)
-            const int cap_m = n_ranges - r0;
+            int m = 0;
+            // layout: start[cap_m] | end[cap_m] | gprefix[cap_m + 1]
+            const int cap_m = (int)std::min<int64_t>((int64_t)n_ranges - r0, (int64_t)MAX_RANGES);
             int64_t *h_start = hs, *h_end = hs + cap_m, *h_pref = hs + 2 * (int64_t)cap_m;
-            while (r1 < n_ranges) {
-                const int64_t len = lens[r1];
-                if (len > chunk_cap) return set_err(TSPLAT_ERR_STATE, "a single range exceeds the scratch capacity");
-                if (acc + len > chunk_cap && m > 0) break;
-                if (len > 0) {
-                    h_start[m] = starts[r1]; h_end[m] = starts[r1] + len; h_pref[m] = groups;
-                    groups += ((starts[r1] + len + 3) >> 2) - (starts[r1] >> 2);
+            while (r0 < n_ranges && m < cap_m && acc < chunk_cap) {
+                const int64_t s0 = starts[r0] + off0;
+                const int64_t left = lens[r0] - off0;
+                const int64_t take = std::min(left, chunk_cap - acc);
+                if (take > 0) {
+                    h_start[m] = s0; h_end[m] = s0 + take; h_pref[m] = groups;
+                    groups += ((s0 + take + 3) >> 2) - (s0 >> 2);
                     ++m;
+                    acc += take;
                 }
-                acc += len;
-                ++r1;
+                if (take == left) { ++r0; off0 = 0; } else off0 += take;
             }
             h_pref[m] = groups;
             if (m > 0) {
@@ -1860,7 +1885,6 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
                 rc = submit(pa, groups, acc);
                 if (rc) return rc;
             }
-            r0 = r1;
         }
     }
     return TSPLAT_OK;
@@ -2058,7 +2082,7 @@ extern "C" int tsplat_content_select(tsplat_ctx *c, const float *image, int res,
     a.hist = reinterpret_cast<unsigned *>(c->d_select);
     int64_t remaining[SELECT_MAX_RANKS];
     for (int r = 0; r < n_ranks; ++r) { if (ranks[r] < 0) return set_err(TSPLAT_ERR_INVALID, "negative rank"); remaining[r] = ranks[r]; }
-    static unsigned h_hist[SELECT_MAX_RANKS * 2048];
+    unsigned *h_hist = c->h_select;
     const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
     for (int pass = 0; pass < 3; ++pass) {
         a.shift = shifts[pass]; a.bits = bits[pass];
