@@ -243,15 +243,31 @@ class PynbodyDataInMemory(ArrayDataLoader):
     def __init__(self, device, snapshot):
         _require_pynbody()
         self.snapshot = snapshot
-        band = lambda b: 10 ** (-0.4 * np.asarray(snapshot[b + "_mag"]))   # noqa: E731
-        try:
-            rgb = np.stack([band('I') * 0.5, band('V'), band('U')], axis=1)
-        except Exception:
-            rgb = None
         boxsize = float(snapshot.properties['boxsize'].in_units("kpc")) if 'boxsize' in snapshot.properties else None
         super().__init__(device, np.asarray(snapshot['pos']), np.asarray(snapshot[self._name_smooth_array]),
-                         np.asarray(snapshot['mass']), quantities=_LazySnapshotArrays(snapshot), rgb=rgb,
+                         np.asarray(snapshot['mass']), quantities=_LazySnapshotArrays(snapshot), rgb=None,
                          position_units=str(snapshot['pos'].units), boxsize=boxsize)
+
+    def _effective_mass_for_band(self, band):
+        return (10 ** (-0.4 * np.asarray(self.snapshot[band + "_mag"])))[self._particle_order]
+
+    def get_rgb_masses(self):
+        # derived on demand, only when the rgb render modes ask for it (reference loader.py:112-121); a snapshot without
+        # the *_mag arrays raises the snapshot's own KeyError, as the reference does
+        rgb = np.empty((len(self), 3), dtype=np.float32)
+        rgb[:, 0] = self._effective_mass_for_band('I') * 0.5
+        rgb[:, 1] = self._effective_mass_for_band('V')
+        rgb[:, 2] = self._effective_mass_for_band('U')
+        rgb[np.isnan(rgb)] = 0.0
+        return rgb
+
+    def get_quantity_label(self, quantity_name):
+        if quantity_name is None:
+            return r"density / $M_{\odot} / \mathrm{kpc}^2$"
+        lunit = self.snapshot[quantity_name].units.latex()
+        if lunit != "":
+            lunit = "$/" + lunit + "$"
+        return quantity_name + lunit
 
     def get_quantity_names(self):
         return self.snapshot.loadable_keys()
