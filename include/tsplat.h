@@ -138,6 +138,21 @@ int tsplat_reduce_colormap(tsplat_ctx *ctx, const float *const *peer_images, int
                            int row0, int nrows, const tsplat_colormap_params *params, const float *lut,
                            int lut_w, int lut_h, void *out, int out_fmt, float *sum_out, void *stream);
 
+/* Multi-GPU image all-reduce for the drop-in classes (no reference counterpart: topsy is single-device; the wiring it
+ * extends is visualizer.py:75-80 loader -> ParticleBuffers and sph.py:306-332 render).  Every rank holds a partial
+ * accumulation image of its particle stripe; this call reduces rows [row0, row0+nrows) over the n_peers partial images
+ * (NVLink peer mappings, HOST array of device pointers) and stores the result into the same rows of EVERY peer's
+ * reduced image (peer_out, HOST array of device pointers): reduce-scatter + all-gather over peer memory in one kernel.
+ *   op == TSPLAT_REDUCE_SUM  out = sum_r (*peer_scale[r]) * peer_images[r]   -- peer_scale[r] is a DEVICE pointer to rank
+ *                            r's mass scale (RenderProgression.end_frame_get_scalefactor) in peer memory, so ranks whose
+ *                            progressive frames covered different fractions of their stripes combine correctly;
+ *   op == TSPLAT_REDUCE_ZMAX surface mode: per pixel the 64-bit (depth, quantity) key maximum (channels must be 2).
+ * The caller brackets the call with barriers (all partial images complete before, all slabs stored after). */
+enum { TSPLAT_REDUCE_SUM = 0, TSPLAT_REDUCE_ZMAX = 1 };
+int tsplat_allreduce_image(tsplat_ctx *ctx, const float *const *peer_images, float *const *peer_out,
+                           const float *const *peer_scale, int n_peers, int channels, int row0, int nrows, int op,
+                           void *stream);
+
 /* Replaces PeriodicSPH's accumulation pass (periodic_sph.py:59-88, overlay.py, shaders/overlay.wgsl): dst (R x R x
  * channels, device) = sum over n <= 128 replicas of weights[i] * src sampled bilinearly at the pixel shifted by the
  * clip-space offset (offsets_xy[2i], offsets_xy[2i+1]); a replica contributes only inside its own [-1,1]^2 + offset
@@ -204,6 +219,18 @@ int64_t tsplat_cell_layout_work_bytes(int64_t n, int nside);
 int tsplat_cell_layout(int device_ordinal, const void *pos, int64_t n, int dtype_bytes, double box_min,
                        double cell_size, int nside, int64_t *order, int64_t *lengths, int32_t *status,
                        void *work, int64_t work_bytes, void *stream);
+
+/* The same with the within-cell shuffle of CellLayout.randomize_within_cells (cell_layout.py:17-24) fused into the
+ * scatter: inside every cell the stable order is permuted by a keyed pseudo-random permutation (4-round Feistel network,
+ * cycle-walked), never across cells, so that any leading fraction of a cell is a fair subsample.  n < 2^31. */
+int tsplat_cell_layout_shuffled(int device_ordinal, const void *pos, int64_t n, int dtype_bytes, double box_min,
+                                double cell_size, int nside, uint32_t shuffle_seed, int64_t *order, int64_t *lengths,
+                                int32_t *status, void *work, int64_t work_bytes, void *stream);
+
+/* dst[i] = (float) src[order[i] * stride + offset] on the device: what the reference's loaders do on the host with
+ * `array.astype(np.float32)[self._particle_order]` (loader.py:100-110).  src is float32 (src_bytes 4) or float64 (8). */
+int tsplat_gather_f32(int device_ordinal, float *dst, const void *src, int src_bytes, int stride, int offset,
+                      const int64_t *order, int64_t n, void *stream);
 
 /* Host <-> device staging for the end-to-end (host buffer) path: thin cudaMemcpyAsync wrappers so the Python host
  * layer needs no other CUDA binding.  Replaces queue.write_buffer / queue.read_texture. */

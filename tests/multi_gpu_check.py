@@ -20,6 +20,86 @@ from topsy_b200.cell_layout import CellLayout         # noqa: E402
 from topsy_b200.colormap import luts                  # noqa: E402
 
 
+def visualizer_check(rank, world):
+    """The drop-in classes under torchrun: every rank's Visualizer loads the same snapshot, keeps its stripe
+    (distributed.shard_loader), splats it and all-reduces the image (distributed.ImageExchange / K6b); images, autorange and
+    presentation must equal those of an unsharded Visualizer of the same snapshot on every rank."""
+    from topsy_b200 import loader
+    from topsy_b200.canvas import offscreen
+    from topsy_b200.drawreason import DrawReason
+    from topsy_b200.visualizer import Visualizer
+
+    def make(sharded, **kw):
+        previous = D.set_sharding(sharded)
+        try:
+            return Visualizer(canvas_class=offscreen.VisualizerCanvas, render_resolution=200, **kw)
+        finally:
+            D.set_sharding(previous)
+
+    cases = [
+        ("density, the reference's 1000-particle fixture", dict(data_loader_args=(1000,)), None, 200.0, "get_sph_image"),
+        ("weighted quantity, fixture with cells", dict(data_loader_args=(20000,), data_loader_kwargs=dict(with_cells=True)),
+         "test-quantity", 20.0, "get_sph_image"),
+        ("rgb", dict(data_loader_args=(5000,), render_mode="rgb"), None, 20.0, "get_sph_image"),
+        ("depth image", dict(data_loader_args=(5000,)), None, 20.0, "get_depth_image"),
+    ]
+    for what, kw, quantity, scale, getter in cases:
+        ref_vis, vis = make(False, **kw), make(True, **kw)
+        assert len(vis.data_loader) < len(ref_vis.data_loader) == vis.data_loader.global_num_particles, what
+        for v in (ref_vis, vis):
+            if quantity is not None:
+                v.quantity_name = quantity
+            v.scale = scale
+            v.rotate(0.2, 0.4)
+        if getter == "get_depth_image":
+            ref_vis._sph.render(DrawReason.EXPORT); vis._sph.render(DrawReason.EXPORT)
+            want, got = ref_vis._sph.get_depth_image(DrawReason.EXPORT), vis._sph.get_depth_image(DrawReason.EXPORT)
+            ok = np.isfinite(want)
+            assert np.array_equal(ok, np.isfinite(got)) and np.abs(got[ok] - want[ok]).max() <= 1e-3 * scale, what
+            continue
+        ref_vis.render_sph(DrawReason.EXPORT); vis.render_sph(DrawReason.EXPORT)
+        want, got = ref_vis._sph.get_image().astype(np.float64), vis._sph.get_image().astype(np.float64)
+        for c in range(want.shape[2]):
+            mag = np.abs(want[..., c])
+            big = mag > 1e-6 * mag.max()
+            if quantity is not None and c == 1:      # signed channel: relative to the accumulated magnitude (see test_gpu_parity)
+                big &= np.abs(want[..., 1]) > 1e-3 * np.abs(want[..., 1]).max()
+            if not big.any():                        # e.g. the all-zero quantity channel of a plain density render
+                assert not got[..., c].any(), (what, c)
+                continue
+            rel = np.abs(got[..., c][big] - want[..., c][big]) / mag[big]
+            assert rel.max() <= 1e-4, (what, c, rel.max())
+        # device autorange and presentation run on the all-reduced image on every rank
+        ref_vis.colormap_autorange(); vis.colormap_autorange()
+        for k in ("vmin", "vmax"):
+            a, b = ref_vis.colormap.get_parameter(k), vis.colormap.get_parameter(k)
+            assert abs(a - b) <= 1e-3 * max(1.0, abs(a)), (what, k, a, b)
+        pa, pb = ref_vis.get_sph_presentation_image(), vis.get_sph_presentation_image()
+        d = np.abs(pa.astype(np.float64) - pb.astype(np.float64))
+        assert d.max() <= (2 if pa.dtype == np.uint8 else 2e-2) and (d > 0).mean() < 2e-2, (what, d.max(), (d > 0).mean())
+    # interactive frames: ranks may cover different fractions of their stripes; the reduce weights them by their mass scale
+    ref_vis, vis = make(False, data_loader_args=(200000,), data_loader_kwargs=dict(with_cells=True)), \
+        make(True, data_loader_args=(200000,), data_loader_kwargs=dict(with_cells=True))
+    for v in (ref_vis, vis):
+        v.scale = 30.0
+    vis._sph._render_progression._recommended_num_particles_to_render = 20000 + 7000 * rank     # force unequal fractions
+    vis.render_sph(DrawReason.CHANGE)
+    frames = 1
+    while vis._sph.needs_refine() and frames < 100:       # collective: true until the slowest rank has drawn its whole stripe
+        vis.render_sph(DrawReason.REFINE); frames += 1
+    assert frames > 1
+    ref_vis.render_sph(DrawReason.EXPORT)
+    want, got = ref_vis._sph.get_image()[..., 0].astype(np.float64), vis._sph.get_image()[..., 0].astype(np.float64)
+    R = want.shape[0]
+    yy, xx = np.mgrid[0:R, 0:R]
+    inside = (xx - R / 2 + 0.5) ** 2 + (yy - R / 2 + 0.5) ** 2 <= (0.6 * R / 2) ** 2      # select_sphere drops far cells in interactive frames
+    big = (want > 1e-6 * want.max()) & inside
+    rel = np.abs(got[big] - want[big]) / want[big]
+    assert rel.max() <= 1e-4, ("progressive", rel.max())
+    if rank == 0:
+        print("VISUALIZER_SHARDING_OK: density / weighted / rgb / depth / progressive equal the unsharded Visualizer")
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -66,6 +146,8 @@ def main():
         sh.close()
     if rank == 0:
         assert np.abs(results["p2p"].astype(int) - results["nccl"].astype(int)).max() <= 1
+    visualizer_check(rank, world)
+    if rank == 0:
         print("MULTI_GPU_CHECK_OK world", world)
     dist.barrier()
     dist.destroy_process_group()

@@ -38,3 +38,88 @@ def test_large_random_and_errors():
         CellLayout.from_positions(torch.from_numpy(pos).cuda(), -10.0, 10.0, 16)
     empty_layout, empty_order = CellLayout.from_positions(torch.zeros((1, 3), device="cuda"), -1.0, 1.0, 4)
     assert empty_layout._lengths.sum() == 1 and empty_order.cpu().numpy().tolist() == [0]
+
+
+def test_device_shuffle_is_a_permutation_inside_every_cell_and_uniform():
+    """Row a4 on the device: the ordering returned with ``shuffle_seed`` permutes the stable ordering inside every cell,
+    never across cells, and a leading fraction of a cell is a fair subsample -- chi-square of where the first 10 % of the
+    shuffled slots came from (deciles of the stable rank), pooled over cells."""
+    rs = np.random.RandomState(21)
+    n = 2_000_003
+    pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+    pos[: n // 4] *= 0.2                                       # a dense clump: cells of very different sizes
+    pos_d = torch.from_numpy(pos).cuda()
+    layout, stable = CellLayout.from_positions(pos_d, -1.001, 1.001, 8)
+    layout2, shuffled = CellLayout.from_positions(pos_d, -1.001, 1.001, 8, shuffle_seed=12345)
+    assert np.array_equal(layout._lengths, layout2._lengths)
+    stable, shuffled = stable.cpu().numpy(), shuffled.cpu().numpy()
+    assert not np.array_equal(stable, shuffled)
+    _, other = CellLayout.from_positions(pos_d, -1.001, 1.001, 8, shuffle_seed=54321)
+    assert not np.array_equal(other.cpu().numpy(), shuffled)   # the seed matters
+    rank_in_cell = np.empty(n, dtype=np.int64)                 # stable rank of every particle inside its cell
+    counts = np.zeros(10)
+    for c in range(layout.get_num_cells()):
+        sl = layout.cell_slice(c)
+        a, b = stable[sl], shuffled[sl]
+        assert np.array_equal(np.sort(b), a)                   # same particles, and `a` is ascending (stable)
+        m = len(a)
+        if m >= 2000:
+            rank_in_cell[a] = np.arange(m)
+            lead = b[: m // 10]
+            counts += np.bincount((rank_in_cell[lead] * 10) // m, minlength=10)
+    expected = counts.sum() / 10
+    chi2 = ((counts - expected) ** 2 / expected).sum()
+    assert chi2 < 27.9, (chi2, counts)                         # 9 degrees of freedom, p = 0.001
+    # neighbouring slots must not stay neighbours: lag-1 correlation of the stable ranks along the shuffled order ~ 0
+    big = int(np.argmax(layout._lengths))
+    sl = layout.cell_slice(big)
+    r = rank_in_cell[shuffled[sl]].astype(np.float64)
+    assert abs(np.corrcoef(r[:-1], r[1:])[0, 1]) < 0.02
+
+
+def test_array_loader_builds_its_layout_on_the_device():
+    """Row a3/a4 wiring (VERDICT r01 missing 4): ArrayDataLoader given a Device runs the cell layout, the within-cell
+    shuffle and the reordering on the GPU; the result is the same partition into cells as the host path, and the rendered
+    image is the same."""
+    from topsy_b200 import loader
+    from topsy_b200.canvas import offscreen
+    from topsy_b200.device import Device
+    from topsy_b200.drawreason import DrawReason
+    from topsy_b200.visualizer import Visualizer
+    rs = np.random.RandomState(2)
+    n = 300_000
+    pos = rs.normal(size=(n, 3)).astype(np.float64) * 3.0
+    smooth = (0.05 * np.exp(rs.normal(size=n) * 0.5)).astype(np.float32)
+    mass = rs.uniform(0.5, 1.5, n).astype(np.float32)
+    q = rs.normal(size=n).astype(np.float32)
+    rgb = rs.uniform(0.1, 1.0, (n, 3)).astype(np.float32)
+    rgb[5, 1] = np.nan
+    dev = Device()
+    on_dev = loader.ArrayDataLoader(dev, pos, smooth, mass, quantities={"q": q}, rgb=rgb)
+    on_host = loader.ArrayDataLoader(dev, pos, smooth, mass, quantities={"q": q}, rgb=rgb, layout_on_device=False)
+    assert on_dev.device_columns(["x", "y", "z", "h"]) is not None and on_host.device_columns(["x"]) is None
+    assert np.array_equal(on_dev._cell_layout._lengths, on_host._cell_layout._lengths)
+    assert len(on_dev) == len(on_host) == n
+    # the same particles cell by cell (mass tags them), every column reordered consistently
+    order_d, order_h = on_dev._particle_order, on_host._particle_order
+    for c in np.flatnonzero(on_host._cell_layout._lengths)[:200]:
+        sl = on_host._cell_layout.cell_slice(c)
+        assert np.array_equal(np.sort(order_d[sl]), np.sort(order_h[sl]))
+    np.testing.assert_array_equal(on_dev.get_positions(), pos.astype(np.float32)[order_d])
+    np.testing.assert_array_equal(on_dev.get_smooth(), smooth[order_d])
+    np.testing.assert_array_equal(on_dev.get_mass(), mass[order_d])
+    np.testing.assert_array_equal(on_dev.get_named_quantity("q"), q[order_d])
+    np.testing.assert_array_equal(on_dev.device_quantity("q").cpu().numpy(), q[order_d])
+    want_rgb = rgb[order_d].copy(); want_rgb[np.isnan(want_rgb)] = 0.0
+    np.testing.assert_array_equal(on_dev.get_rgb_masses(), want_rgb)
+    images = []
+    for flag in (None, False):
+        vis = Visualizer(data_loader_class=loader.ArrayDataLoader, data_loader_args=(pos, smooth, mass),
+                         data_loader_kwargs={"quantities": {"q": q}, "layout_on_device": flag}, render_resolution=256,
+                         canvas_class=offscreen.VisualizerCanvas)
+        vis.quantity_name = "q"
+        vis.scale = 6.0
+        vis.render_sph(DrawReason.EXPORT)
+        images.append(vis._sph.get_image().astype(np.float64))
+    big = images[1][..., 0] > 1e-6 * images[1][..., 0].max()
+    assert (np.abs(images[0][..., 0][big] - images[1][..., 0][big]) / images[1][..., 0][big]).max() <= 1e-4

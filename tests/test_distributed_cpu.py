@@ -98,3 +98,43 @@ def test_image_sum_over_gloo_world_of_two():
     want = got[0][2] + got[1][2]
     np.testing.assert_allclose(got[0][1], want, rtol=1e-6)
     np.testing.assert_allclose(got[1][1], want, rtol=1e-6)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shard_loader_stripes_partition_the_snapshot(world):
+    """distributed.shard_loader: every rank keeps its per-cell stripe; the stripes partition the snapshot and each
+    rank's loader (len, getters, cell layout, progression) describes exactly its stripe."""
+    from topsy_b200 import loader
+    rs = np.random.RandomState(8)
+    n = 5000
+    pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+    smooth = rs.uniform(0.01, 0.1, n).astype(np.float32)
+    mass = np.arange(n, dtype=np.float32)                      # a unique tag per particle
+    q = rs.normal(size=n).astype(np.float32)
+    np.random.seed(3)
+    seen = np.zeros(n, int)
+    for rank in range(world):
+        np.random.seed(3)                                        # same within-cell shuffle on every rank
+        ld = loader.ArrayDataLoader(None, pos, smooth, mass, quantities={"q": q}, nside=4)
+        full_lengths = ld._cell_layout._lengths.copy()
+        D.shard_loader(ld, rank, world)
+        assert ld.global_num_particles == n
+        assert len(ld) == D.shard_cell_lengths(full_lengths, rank, world).sum()
+        tags = ld.get_mass().astype(int)
+        seen[tags] += 1
+        np.testing.assert_array_equal(ld.get_positions(), pos[tags])
+        np.testing.assert_array_equal(ld.get_named_quantity("q"), q[tags])
+        np.testing.assert_array_equal(ld._cell_layout._lengths, D.shard_cell_lengths(full_lengths, rank, world))
+        assert ld.get_render_progression()._cell_layout.get_num_particles() == len(ld)
+        # particles of the stripe are still grouped by cell
+        sl = ld._cell_layout.cell_slice(int(np.argmax(ld._cell_layout._lengths)))
+        cell_pos = ld.get_positions()[sl]
+        assert np.ptp(cell_pos, axis=0).max() <= 2.0 * 1.05 / 4 + 1e-6
+    assert (seen == 1).all()
+    # a loader without cells: every world-th particle
+    t0 = loader.TestDataLoader(None, 1000)
+    t1 = loader.TestDataLoader(None, 1000)
+    D.shard_loader(t1, 1, world)
+    np.testing.assert_array_equal(t1.get_positions(), t0.get_positions()[1::world])
+    np.testing.assert_array_equal(t1.get_smooth(), t0.get_smooth()[1::world])
+    assert len(t1.get_mass()) == len(t1) == len(range(1, 1000, world))

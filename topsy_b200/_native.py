@@ -57,6 +57,8 @@ _lib = None
 
 _vp, _i64, _i32, _f = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
+REDUCE_SUM, REDUCE_ZMAX = 0, 1
+
 _SIGNATURES = {
     "tsplat_last_error": (ctypes.c_char_p, []),
     "tsplat_abi_version": (_i32, []),
@@ -75,6 +77,8 @@ _SIGNATURES = {
                                _i32, _vp]),
     "tsplat_reduce_colormap": (_i32, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i32, _i32, ctypes.POINTER(ColormapParams), _vp,
                                       _i32, _i32, _vp, _i32, _vp, _vp]),
+    "tsplat_allreduce_image": (_i32, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i32, _i32, _i32, _i32,
+                                      _i32, _vp]),
     "tsplat_set_surface": (_i32, [_vp, _vp, _i32, _f]),
     "tsplat_bilateral_filter": (_i32, [_vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "tsplat_surface_shade": (_i32, [_vp, _vp, _i32, ctypes.POINTER(SurfaceParams), _vp, _i32, _vp, _i32, _i32, _i32, _vp]),
@@ -85,6 +89,9 @@ _SIGNATURES = {
     "tsplat_cell_layout_work_bytes": (_i64, [_i64, _i32]),
     "tsplat_cell_layout": (_i32, [_i32, _vp, _i64, _i32, ctypes.c_double, ctypes.c_double, _i32, _vp, _vp, _vp, _vp,
                                   _i64, _vp]),
+    "tsplat_cell_layout_shuffled": (_i32, [_i32, _vp, _i64, _i32, ctypes.c_double, ctypes.c_double, _i32, ctypes.c_uint32, _vp, _vp,
+                                           _vp, _vp, _i64, _vp]),
+    "tsplat_gather_f32": (_i32, [_i32, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp]),
     "tsplat_memcpy_h2d": (_i32, [_vp, _vp, _i64, _vp]),
     "tsplat_memcpy_d2h": (_i32, [_vp, _vp, _i64, _vp]),
     "tsplat_stream_sync": (_i32, [_vp]),

@@ -73,14 +73,20 @@ class CellLayout:
         return cell_size, centres
 
     @classmethod
-    def from_positions(cls, particle_positions, box_min: float, box_max: float, nside: int):
+    def from_positions(cls, particle_positions, box_min: float, box_max: float, nside: int, shuffle_seed=None):
         """Returns ``(layout, ordering)`` where ``positions[ordering]`` is cell-sorted.
 
         ``particle_positions`` is an (N,3) numpy array, or an (N,3) torch CUDA tensor (then the ordering is returned
         as a CUDA int64 tensor and all O(N) work runs on the device).  Raises ValueError when a particle is outside
-        the box, like the reference (cell_layout.py:83-84, :100-101)."""
+        the box, like the reference (cell_layout.py:83-84, :100-101).
+
+        ``shuffle_seed`` (device tensors only): fuse ``randomize_within_cells`` into the sort -- the returned ordering is
+        already shuffled inside every cell (a keyed pseudo-random permutation per cell, computed slot by slot on the
+        device), i.e. it equals ``ordering[layout.randomize_within_cells()]`` in distribution."""
         if _is_cuda_tensor(particle_positions):
-            return cls._from_positions_device(particle_positions, box_min, box_max, nside)
+            return cls._from_positions_device(particle_positions, box_min, box_max, nside, shuffle_seed)
+        if shuffle_seed is not None:
+            raise ValueError("shuffle_seed needs device-resident positions; use randomize_within_cells() on the host")
 
         pos = particle_positions
         if pos.min() < box_min or pos.max() >= box_max:
@@ -98,7 +104,7 @@ class CellLayout:
         return cls(centres, offsets, lengths), ordering
 
     @classmethod
-    def _from_positions_device(cls, pos, box_min, box_max, nside):
+    def _from_positions_device(cls, pos, box_min, box_max, nside, shuffle_seed=None):
         import ctypes
 
         import torch
@@ -129,11 +135,19 @@ class CellLayout:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         work = torch.empty(lib.tsplat_cell_layout_work_bytes(n, nside), dtype=torch.uint8, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        N.check(lib.tsplat_cell_layout(dev.index, ctypes.c_void_p(pos.data_ptr()), n, pos.element_size(),
-                                       ctypes.c_double(float(sub_min)), ctypes.c_double(float(cell_size)), nside,
-                                       ctypes.c_void_p(order.data_ptr()), ctypes.c_void_p(lengths.data_ptr()),
-                                       ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()),
-                                       work.numel(), stream))
+        if shuffle_seed is None:
+            N.check(lib.tsplat_cell_layout(dev.index, ctypes.c_void_p(pos.data_ptr()), n, pos.element_size(),
+                                           ctypes.c_double(float(sub_min)), ctypes.c_double(float(cell_size)), nside,
+                                           ctypes.c_void_p(order.data_ptr()), ctypes.c_void_p(lengths.data_ptr()),
+                                           ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()),
+                                           work.numel(), stream))
+        else:
+            N.check(lib.tsplat_cell_layout_shuffled(dev.index, ctypes.c_void_p(pos.data_ptr()), n, pos.element_size(),
+                                                    ctypes.c_double(float(sub_min)), ctypes.c_double(float(cell_size)), nside,
+                                                    int(shuffle_seed) & 0xffffffff or 1,
+                                                    ctypes.c_void_p(order.data_ptr()), ctypes.c_void_p(lengths.data_ptr()),
+                                                    ctypes.c_void_p(status.data_ptr()), ctypes.c_void_p(work.data_ptr()),
+                                                    work.numel(), stream))
         if int(status.item()) != 0:
             raise ValueError("Particle positions are too close to edge of box; expand box size")
         lengths_h = lengths.cpu().numpy().astype(np.intp)

@@ -112,6 +112,7 @@ struct tsplat_ctx {
     int sm_count;
     bool bin_attr_set;
     bool gather_attr_set[4];
+    size_t bilateral_smem_set;   // largest dynamic shared-memory size k_bilateral_filter has been opted into
 };
 
 extern "C" const char *tsplat_last_error(void) { return g_err; }
@@ -1331,6 +1332,55 @@ __global__ void __launch_bounds__(256) k_reduce_colormap(const ReduceArgs a)
     if (a.out) store_rgba(a.out, pix, a.out_fmt, colormap_value(v, a.p, a.lut, a.lut_w, a.lut_h));
 }
 
+// K6b: image all-reduce over NVLink peer memory for the drop-in classes: every rank reduces its slab of rows over all
+// partial images and stores the result into every peer's reduced image (reduce-scatter + all-gather in one kernel).
+struct AllReduceArgs {
+    const float *peer[MAX_PEERS];
+    float *out[MAX_PEERS];
+    const float *scale[MAX_PEERS];
+    int n_peers, op;
+    int64_t first, count;      // slab as a range of floats of the flattened (R, R, C) image
+};
+
+__global__ void __launch_bounds__(256) k_allreduce_image(const AllReduceArgs a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (a.op == TSPLAT_REDUCE_ZMAX) {           // (quantity, depth) pixels as 64-bit keys, depth in the high word
+        const int64_t n2 = a.count >> 1;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+            unsigned long long best = 0ull;
+            for (int r = 0; r < a.n_peers; ++r)
+                best = max(best, reinterpret_cast<const unsigned long long *>(a.peer[r] + a.first)[i]);
+            for (int r = 0; r < a.n_peers; ++r) reinterpret_cast<unsigned long long *>(a.out[r] + a.first)[i] = best;
+        }
+        return;
+    }
+    float w[MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r) w[r] = r < a.n_peers ? *a.scale[r] : 0.0f;
+    if (((a.first | a.count) & 3) == 0) {       // 128-bit path (rows of R * C floats: a multiple of 4 for every usual R)
+        const int64_t n4 = a.count >> 2;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; ++r)
+                if (r < a.n_peers) {
+                    const float4 t = reinterpret_cast<const float4 *>(a.peer[r] + a.first)[i];
+                    v.x += w[r] * t.x; v.y += w[r] * t.y; v.z += w[r] * t.z; v.w += w[r] * t.w;
+                }
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; ++r)
+                if (r < a.n_peers) reinterpret_cast<float4 *>(a.out[r] + a.first)[i] = v;
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += stride) {
+            float v = 0.0f;
+            for (int r = 0; r < a.n_peers; ++r) v += w[r] * a.peer[r][a.first + i];
+            for (int r = 0; r < a.n_peers; ++r) a.out[r][a.first + i] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K7: periodic tiling -- out = sum_i w_i * image shifted by offset_i (reference: periodic_sph.py:16-88 draws the SPH
 // texture as <= 125 instanced quads through overlay.wgsl with a linear sampler and ONE/ONE blending)
@@ -1946,7 +1996,16 @@ extern "C" int tsplat_bilateral_filter(tsplat_ctx *c, const float *in, float *ou
     a.in = in; a.out = out; a.width = width; a.height = height; a.spatial_sigma = spatial_sigma; a.range_sigma = range_sigma;
     a.kernel_size = kernel_size;
     dim3 grid((width + 31) / 32, (height + 7) / 8);
-    tsplat_surface::k_bilateral_filter<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    const size_t smem = tsplat_surface::bilateral_smem_bytes(kernel_size / 2);
+    if (smem <= 200 * 1024) {
+        if (smem > 48 * 1024 && smem > c->bilateral_smem_set) {
+            CUDA_TRY(cudaFuncSetAttribute(tsplat_surface::k_bilateral_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c->bilateral_smem_set = smem;
+        }
+        tsplat_surface::k_bilateral_filter<<<grid, tsplat_surface::BF_TX * tsplat_surface::BF_TY, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        tsplat_surface::k_bilateral_filter_direct<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    }
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());
@@ -1998,6 +2057,39 @@ extern "C" int tsplat_reduce_colormap(tsplat_ctx *c, const float *const *peer_im
     a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_fmt = out_fmt; a.sum_out = sum_out;
     dim3 grid((c->R + 255) / 256, nrows);
     k_reduce_colormap<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    c->launches++;
+    c->last_stream = (cudaStream_t)stream;
+    CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_allreduce_image(tsplat_ctx *c, const float *const *peer_images, float *const *peer_out,
+                                      const float *const *peer_scale, int n_peers, int channels, int row0, int nrows, int op,
+                                      void *stream)
+{
+    if (!c || !peer_images || !peer_out) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    if (n_peers < 1 || n_peers > MAX_PEERS) return set_err(TSPLAT_ERR_INVALID, "n_peers must be in [1, %d]", MAX_PEERS);
+    if (channels != 1 && channels != 2 && channels != 4) return set_err(TSPLAT_ERR_INVALID, "channels must be 1, 2 or 4");
+    if (row0 < 0 || nrows < 0 || row0 + nrows > c->R) return set_err(TSPLAT_ERR_INVALID, "row slab outside the image");
+    if (op != TSPLAT_REDUCE_SUM && op != TSPLAT_REDUCE_ZMAX) return set_err(TSPLAT_ERR_INVALID, "unknown reduction %d", op);
+    if (op == TSPLAT_REDUCE_ZMAX && channels != 2) return set_err(TSPLAT_ERR_INVALID, "the z-buffer reduction needs a 2-channel image");
+    if (op == TSPLAT_REDUCE_SUM && !peer_scale) return set_err(TSPLAT_ERR_INVALID, "peer scales missing");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (nrows == 0) return TSPLAT_OK;
+    AllReduceArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_images[r] || !peer_out[r] || (op == TSPLAT_REDUCE_SUM && !peer_scale[r]))
+            return set_err(TSPLAT_ERR_INVALID, "NULL peer pointer %d", r);
+        a.peer[r] = peer_images[r]; a.out[r] = peer_out[r]; a.scale[r] = op == TSPLAT_REDUCE_SUM ? peer_scale[r] : nullptr;
+    }
+    a.n_peers = n_peers; a.op = op;
+    a.first = (int64_t)row0 * c->R * channels;
+    a.count = (int64_t)nrows * c->R * channels;
+    int64_t blocks = (a.count / 4 + 255) / 256;
+    if (blocks > (int64_t)c->sm_count * 8) blocks = (int64_t)c->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    k_allreduce_image<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());

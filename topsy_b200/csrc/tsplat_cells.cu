@@ -116,9 +116,40 @@ __global__ void __launch_bounds__(1024) k_cell_offsets(const int64_t *__restrict
     for (int i = b; i < b + per && i < ncell; ++i) { offsets[i] = run; run += lengths[i]; }
 }
 
+__device__ __forceinline__ unsigned mix32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// A keyed pseudo-random PERMUTATION of [0, n): 4-round Feistel network on the smallest even number of bits that holds n,
+// cycle-walked back into range (at most 4 n candidates, so < 4 walks on average).  Every slot computes its image on its
+// own: the within-cell shuffle of CellLayout.randomize_within_cells (cell_layout.py:17-24) without a sort.
+__device__ __forceinline__ unsigned feistel_permute(unsigned r, unsigned n, unsigned key)
+{
+    if (n <= 1u) return 0u;
+    unsigned bits = 32u - (unsigned)__clz(n - 1u);
+    if (bits < 2u) bits = 2u;
+    bits += bits & 1u;
+    const unsigned half = bits >> 1, mask = (1u << half) - 1u;
+    do {
+        unsigned L = r >> half, R = r & mask;
+#pragma unroll
+        for (unsigned round = 0; round < 4u; ++round) {
+            const unsigned t = L ^ (mix32(R ^ key ^ (round * 0x9e3779b9u)) & mask);
+            L = R; R = t;
+        }
+        r = (L << half) | R;
+    } while (r >= n);
+    return r;
+}
+
+// shuffle_seed == 0: stable order (== np.argsort(kind='stable')); otherwise slot s of cell c goes to
+// feistel_permute(s, lengths[c], hash(seed, c)): a pseudo-random permutation inside every cell, never across cells
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_cell_scatter(const int *__restrict__ keys, int64_t n, int64_t per_warp, int units,
                                                                   unsigned int *__restrict__ table,
                                                                   const int64_t *__restrict__ offsets,
+                                                                  const int64_t *__restrict__ lengths, unsigned shuffle_seed,
                                                                   int64_t *__restrict__ order)
 {
     const int unit = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -138,13 +169,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_cell_scatter(const int *
             unsigned int base = 0;
             if (lane == leader) base = atomicAdd(&table[(size_t)key * units + unit], (unsigned)__popc(peers));
             base = __shfl_sync(peers, base, leader);
-            order[offsets[key] + base + rank] = i;
+            unsigned slot = base + (unsigned)rank;
+            if (shuffle_seed) slot = feistel_permute(slot, (unsigned)lengths[key], mix32(shuffle_seed ^ mix32((unsigned)key + 0x632be5abu)));
+            order[offsets[key] + slot] = i;
         }
         __syncwarp();
     }
 }
-
-thread_local char g_cell_err[256] = "";
 
 }  // namespace
 
@@ -154,9 +185,9 @@ extern "C" int64_t tsplat_cell_layout_work_bytes(int64_t n, int nside)
     return make_plan(n, nside).total;
 }
 
-extern "C" int tsplat_cell_layout(int device_ordinal, const void *pos, int64_t n, int dtype_bytes, double box_min,
-                                  double cell_size, int nside, int64_t *order, int64_t *lengths, int32_t *status,
-                                  void *work, int64_t work_bytes, void *stream)
+static int cell_layout_impl(int device_ordinal, const void *pos, int64_t n, int dtype_bytes, double box_min,
+                            double cell_size, int nside, unsigned shuffle_seed, int64_t *order, int64_t *lengths, int32_t *status,
+                            void *work, int64_t work_bytes, void *stream)
 {
     if (n < 0 || nside <= 0 || nside > 1024 || (dtype_bytes != 4 && dtype_bytes != 8)) return TSPLAT_ERR_INVALID;
     if (!lengths || !status || !work || (n > 0 && (!pos || !order))) return TSPLAT_ERR_INVALID;
@@ -182,7 +213,52 @@ extern "C" int tsplat_cell_layout(int device_ordinal, const void *pos, int64_t n
     }
     k_cell_units<<<ncell, 256, 0, st>>>(table, p.units, lengths);
     k_cell_offsets<<<1, 1024, 0, st>>>(lengths, ncell, offsets);
-    if (n > 0) k_cell_scatter<<<grid, WARPS_PER_CTA * 32, 0, st>>>(keys, n, p.per_warp, p.units, table, offsets, order);
+    if (n > 0)
+        k_cell_scatter<<<grid, WARPS_PER_CTA * 32, 0, st>>>(keys, n, p.per_warp, p.units, table, offsets, lengths, shuffle_seed, order);
+    if (cudaGetLastError() != cudaSuccess) return TSPLAT_ERR_CUDA;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_cell_layout(int device_ordinal, const void *pos, int64_t n, int dtype_bytes, double box_min,
+                                  double cell_size, int nside, int64_t *order, int64_t *lengths, int32_t *status,
+                                  void *work, int64_t work_bytes, void *stream)
+{
+    return cell_layout_impl(device_ordinal, pos, n, dtype_bytes, box_min, cell_size, nside, 0u, order, lengths, status, work,
+                            work_bytes, stream);
+}
+
+extern "C" int tsplat_cell_layout_shuffled(int device_ordinal, const void *pos, int64_t n, int dtype_bytes, double box_min,
+                                           double cell_size, int nside, uint32_t shuffle_seed, int64_t *order, int64_t *lengths,
+                                           int32_t *status, void *work, int64_t work_bytes, void *stream)
+{
+    if (n >= ((int64_t)1 << 31)) return TSPLAT_ERR_INVALID;      // slots inside a cell are permuted as 32-bit numbers
+    return cell_layout_impl(device_ordinal, pos, n, dtype_bytes, box_min, cell_size, nside, shuffle_seed ? shuffle_seed : 1u, order,
+                            lengths, status, work, work_bytes, stream);
+}
+
+// dst[i] = (float) src[order[i] * stride + offset]: the loaders' "array[ordering]" (loader.py:100-110 of the reference) on
+// the device; src is float32 (src_bytes 4) or float64 (8)
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_f32(float *__restrict__ dst, const T *__restrict__ src, const int64_t *__restrict__ order,
+                                                   int64_t n, int stride, int offset)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[order[i] * stride + offset];
+}
+
+extern "C" int tsplat_gather_f32(int device_ordinal, float *dst, const void *src, int src_bytes, int stride, int offset,
+                                 const int64_t *order, int64_t n, void *stream)
+{
+    if (n < 0 || stride < 1 || offset < 0 || offset >= stride || (src_bytes != 4 && src_bytes != 8)) return TSPLAT_ERR_INVALID;
+    if (n > 0 && (!dst || !src || !order)) return TSPLAT_ERR_INVALID;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return TSPLAT_ERR_CUDA;
+    if (n == 0) return TSPLAT_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (src_bytes == 4)
+        k_gather_f32<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, static_cast<const float *>(src), order, n, stride, offset);
+    else
+        k_gather_f32<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, static_cast<const double *>(src), order, n, stride, offset);
     if (cudaGetLastError() != cudaSuccess) return TSPLAT_ERR_CUDA;
     return TSPLAT_OK;
 }

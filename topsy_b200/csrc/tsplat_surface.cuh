@@ -161,8 +161,17 @@ __global__ void __launch_bounds__(256) k_queue_surface(const QueueArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K10: bilateral filter of the depth channel (smooth.wgsl:13-48).  fp32, same operation order as the shader:
-// rows outer, columns inner; channel 0 passes through.
+// K10: bilateral filter of the depth channel (replaces shaders/smooth.wgsl, colormap/surface.py:262-297); channel 0
+// passes through.  out = sum_taps s w / sum_taps w over the (2 half + 1)^2 clamp-to-edge window, w = w_spatial(dx, dy) *
+// exp(-(s - centre)^2 / (2 sigma_r^2)).
+//
+// B200 design: a CTA produces a 32 x 8 block of outputs from a shared-memory tile of the depth channel with its halo
+// ((8 + 2 half) x (32 + 2 half) floats, clamp-to-edge resolved once while staging), so every input texel is fetched from
+// global memory once per CTA instead of (2 half + 1)^2 times per pixel; the spatial weights depend only on (|dx|, |dy|)
+// and are tabulated once per CTA in shared memory with the reference's own operations (sqrt, square, exp), which leaves
+// ONE exp and one division per tap instead of two exps, a sqrt and two divisions.  Taps are accumulated per pixel in the
+// reference's order (rows outer, columns inner) with separate multiplies and adds, so the result is bit-identical to the
+// direct evaluation (kept below as the fallback for windows whose tile does not fit in shared memory).
 // ------------------------------------------------------------------------------------------------------------
 struct BilateralArgs {
     const float *in;
@@ -172,7 +181,55 @@ struct BilateralArgs {
     int kernel_size;
 };
 
-__global__ void __launch_bounds__(256) k_bilateral_filter(const BilateralArgs a)
+constexpr int BF_TX = 32, BF_TY = 8;
+
+__host__ __device__ inline size_t bilateral_smem_bytes(int half)
+{
+    return sizeof(float) * ((size_t)(BF_TY + 2 * half) * (BF_TX + 2 * half) + (size_t)(half + 1) * (half + 1));
+}
+
+__global__ void __launch_bounds__(BF_TX * BF_TY) k_bilateral_filter(const BilateralArgs a)
+{
+    extern __shared__ float bf_smem[];
+    const int half = a.kernel_size / 2;
+    const int tw = BF_TX + 2 * half, th = BF_TY + 2 * half;
+    float *tile = bf_smem, *wtab = bf_smem + (size_t)tw * th;
+    const int x0 = blockIdx.x * BF_TX, y0 = blockIdx.y * BF_TY;
+    const float2 *in = reinterpret_cast<const float2 *>(a.in);
+    const float two_ss = 2.0f * a.spatial_sigma * a.spatial_sigma, two_rs = 2.0f * a.range_sigma * a.range_sigma;
+    for (int i = threadIdx.x; i < tw * th; i += BF_TX * BF_TY) {
+        const int r = i / tw, c = i - r * tw;
+        const int sy = min(max(y0 - half + r, 0), a.height - 1), sx = min(max(x0 - half + c, 0), a.width - 1);
+        tile[i] = __ldg(&in[(size_t)sy * a.width + sx].y);
+    }
+    for (int i = threadIdx.x; i < (half + 1) * (half + 1); i += BF_TX * BF_TY) {
+        const int ady = i / (half + 1), adx = i - ady * (half + 1);
+        const float dist = sqrtf((float)(adx * adx + ady * ady));
+        wtab[i] = expf(-(dist * dist) / two_ss);
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & (BF_TX - 1), ty = threadIdx.x / BF_TX;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= a.width || y >= a.height) return;
+    const float centre = tile[(ty + half) * tw + tx + half];
+    float vsum = 0.0f, wsum = 0.0f;
+    for (int dy = -half; dy <= half; ++dy) {
+        const float *row = tile + (ty + half + dy) * tw + tx + half;
+        const float *wrow = wtab + abs(dy) * (half + 1);
+        for (int dx = -half; dx <= half; ++dx) {
+            const float s = row[dx];
+            const float diff = fabsf(s - centre);
+            const float w = wrow[abs(dx)] * expf(-(diff * diff) / two_rs);
+            vsum += s * w;
+            wsum += w;
+        }
+    }
+    const size_t o = (size_t)y * a.width + x;
+    reinterpret_cast<float2 *>(a.out)[o] = make_float2(in[o].x, vsum / wsum);
+}
+
+// direct evaluation from global memory: windows too large for a shared-memory tile (kernel_size > ~200)
+__global__ void __launch_bounds__(256) k_bilateral_filter_direct(const BilateralArgs a)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= a.width || y >= a.height) return;
@@ -187,10 +244,8 @@ __global__ void __launch_bounds__(256) k_bilateral_filter(const BilateralArgs a)
             const int sx = min(max(x + dx, 0), a.width - 1);
             const float s = __ldg(&in[(size_t)sy * a.width + sx].y);
             const float dist = sqrtf((float)(dx * dx + dy * dy));
-            const float w_spatial = expf(-(dist * dist) / two_ss);
             const float diff = fabsf(s - centre.y);
-            const float w_range = expf(-(diff * diff) / two_rs);
-            const float w = w_spatial * w_range;
+            const float w = expf(-(dist * dist) / two_ss) * expf(-(diff * diff) / two_rs);
             vsum += s * w;
             wsum += w;
         }

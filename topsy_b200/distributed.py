@@ -51,6 +51,57 @@ def row_slab(resolution: int, rank: int, world: int):
     return row0, base + (1 if rank < extra else 0)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# sharding of the drop-in classes (Visualizer / loaders / SPH) under torchrun
+# ----------------------------------------------------------------------------------------------------------------
+_sharding_enabled = True
+
+
+def set_sharding(enabled: bool):
+    """Switch the automatic sharding of the drop-in classes on / off (e.g. to build an unsharded reference Visualizer
+    inside a multi-rank test).  Returns the previous setting."""
+    global _sharding_enabled
+    previous, _sharding_enabled = _sharding_enabled, bool(enabled)
+    return previous
+
+
+def shard_context(group=None):
+    """(rank, world) the drop-in classes shard over: the default process group when torch.distributed is initialised
+    with more than one rank and sharding is enabled, else (0, 1)."""
+    if not _sharding_enabled:
+        return 0, 1
+    try:
+        import torch.distributed as dist
+    except ImportError:      # pragma: no cover
+        return 0, 1
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    world = dist.get_world_size(group)
+    return (dist.get_rank(group), world) if world > 1 else (0, 1)
+
+
+def shard_loader(loader, rank: int, world: int):
+    """Keep only ``rank``'s stripe of a data loader: every ``world``-th particle of every cell of its cell layout (or of
+    the whole snapshot when the loader has no cells).  The loader keeps working as before -- ``len``, the getters and
+    ``get_render_progression`` now describe the stripe -- and remembers the global particle count in
+    ``loader.global_num_particles``."""
+    from .cell_layout import CellLayout
+    n = len(loader)
+    if world <= 1:
+        loader.global_num_particles = n
+        return loader
+    layout = getattr(loader, "_cell_layout", None)
+    if layout is not None:
+        mine = shard_indices(layout._offsets, layout._lengths, rank, world)
+        lengths = shard_cell_lengths(layout._lengths, rank, world).astype(layout._lengths.dtype)
+        loader._cell_layout = CellLayout(layout._centres, np.cumsum(lengths) - lengths, lengths)
+    else:
+        mine = np.arange(rank, n, world, dtype=np.int64)
+    loader._keep_particles(mine)
+    loader.global_num_particles = n
+    return loader
+
+
 def reduce_image_host(image, group=None, dst: int | None = None):
     """Sum a partial image over the process group with the backend's collective (NCCL on CUDA tensors, gloo on CPU)."""
     import torch.distributed as dist
@@ -64,6 +115,74 @@ def reduce_image_host(image, group=None, dst: int | None = None):
 # ----------------------------------------------------------------------------------------------------------------
 # device side
 # ----------------------------------------------------------------------------------------------------------------
+class ImageExchange:
+    """Partial + reduced accumulation image of one renderer on every rank, and the all-reduce between them.
+
+    'p2p'  (NVLink boxes): both images and a one-float mass-scale slot live in PyTorch symmetric memory; ``allreduce`` is
+           barrier -> tsplat_allreduce_image (every rank reduces its slab of rows over all peers' partial images, weighted
+           by each peer's mass scale, and stores it into every peer's reduced image) -> barrier.
+    'nccl' fallback where peer access is not available: all_reduce of scale * partial.
+    Construction is collective: every rank must create its exchanges in the same order."""
+
+    def __init__(self, engine, resolution: int, channels: int, group=None, method: str = "auto"):
+        import torch
+        import torch.distributed as dist
+        self.engine = engine
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.resolution, self.channels = resolution, channels
+        self.device = engine.device
+        shape = (resolution, resolution, channels)
+        self.method = method
+        if method in ("auto", "p2p"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                gname = (group or dist.group.WORLD).group_name
+                self.partial = symm.empty(shape, dtype=torch.float32, device=self.device)
+                self.reduced = symm.empty(shape, dtype=torch.float32, device=self.device)
+                self._scale = symm.empty((4,), dtype=torch.float32, device=self.device)
+                self._hdl = symm.rendezvous(self.partial, gname)
+                hdl_r = symm.rendezvous(self.reduced, gname)
+                hdl_s = symm.rendezvous(self._scale, gname)
+                self.partial.zero_(); self.reduced.zero_(); self._scale.fill_(1.0)
+                arr = ctypes.c_void_p * self.world
+                self._peer_partial = arr(*[int(p) for p in self._hdl.buffer_ptrs])
+                self._peer_reduced = arr(*[int(p) for p in hdl_r.buffer_ptrs])
+                self._peer_scale = arr(*[int(p) for p in hdl_s.buffer_ptrs])
+                self.method = "p2p"
+            except Exception as e:
+                if method == "p2p":
+                    raise
+                self.method = "nccl"
+                self._fallback_reason = repr(e)
+        if self.method == "nccl":
+            self.partial = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            self.reduced = torch.zeros(shape, dtype=torch.float32, device=self.device)
+
+    def allreduce(self, mass_scale: float, zmax: bool = False):
+        """reduced (on every rank) = sum over ranks of mass_scale_r * partial_r   (zmax: per-pixel z-buffer maximum)."""
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        if self.method == "p2p":
+            self._scale.fill_(float(mass_scale))
+            self._hdl.barrier()                       # every partial image and scale is complete and visible
+            row0, nrows = row_slab(self.resolution, self.rank, self.world)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            N.check(self.engine.lib.tsplat_allreduce_image(self.engine._ctx, self._peer_partial, self._peer_reduced,
+                                                           self._peer_scale, self.world, self.channels, row0, nrows,
+                                                           N.REDUCE_ZMAX if zmax else N.REDUCE_SUM, stream))
+            self._hdl.barrier()                       # every slab of every reduced image has been stored
+        elif zmax:
+            keys = self.partial.view(torch.int64).clone()     # (quantity, depth) pixels as 64-bit keys, depth high
+            dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=self.group)
+            self.reduced.copy_(keys.view(torch.float32).view_as(self.reduced))
+        else:
+            torch.mul(self.partial, float(mass_scale), out=self.reduced)
+            dist.all_reduce(self.reduced, op=dist.ReduceOp.SUM, group=self.group)
+        return self.reduced
+
+
 class ShardedSplat:
     """One rank of a sharded render: local engine + the image exchange."""
 

@@ -67,6 +67,11 @@ class AbstractDataLoader(ABC):
         period = self.get_periodicity_scale()
         return period / 2 if period is not None else config.DEFAULT_SCALE
 
+    def _keep_particles(self, indices):
+        """Drop every particle not in ``indices`` (ascending positions in the loader's current order): how a rank of a
+        multi-GPU run keeps its stripe (topsy_b200.distributed.shard_loader).  No reference counterpart."""
+        raise TypeError(f"{type(self).__name__} does not support multi-GPU sharding")
+
 
 class TestDataLoader(AbstractDataLoader):
     """Three-component Gaussian mixture with h = 2 / (number density)^(1/3)  (loader.py:241-332).
@@ -115,6 +120,11 @@ class TestDataLoader(AbstractDataLoader):
             den += weight * np.exp(-np.sum((pos - mean) ** 2 / std ** 2, axis=1)) / ((2 * np.pi) ** 1.5 * np.prod(std))
         return den * self._n_particles
 
+    def _keep_particles(self, indices):
+        self._gmm_pos = self._gmm_pos[indices]
+        self._gmm_den = self._gmm_den[indices]
+        self._n_particles = len(indices)
+
     def get_positions(self):
         return self._gmm_pos
 
@@ -161,7 +171,7 @@ class ArrayDataLoader(AbstractDataLoader):
     bounding cube by CELL_LAYOUT_FRACTIONAL_PADDING, bucket into DEFAULT_CELLS_NSIDE^3 cells, shuffle inside cells."""
 
     def __init__(self, device, pos, smooth, mass, quantities=None, rgb=None, position_units="kpc", boxsize=None,
-                 use_cells=True, nside=None):
+                 use_cells=True, nside=None, layout_on_device=None):
         super().__init__(device)
         pos = np.asarray(pos)
         n = len(pos)
@@ -171,29 +181,127 @@ class ArrayDataLoader(AbstractDataLoader):
         lo = pos.min(); hi = pos.max()
         extent = hi - lo
         self._initial_view_width = extent
+        self._dev = None                  # device-resident columns (x, y, z, h, m [, r, g, b]) when the layout ran on the GPU
+        self._order_dev = None
+        if layout_on_device is None:      # default: on the GPU whenever the loader was given one
+            layout_on_device = use_cells and hasattr(device, "torch_device") and n > 0
+        if use_cells and layout_on_device:
+            self._init_on_device(pos, smooth, mass, rgb, lo, hi, extent, nside or config.DEFAULT_CELLS_NSIDE)
+            return
         if use_cells:
             lo = lo - config.CELL_LAYOUT_FRACTIONAL_PADDING * extent
             hi = hi + config.CELL_LAYOUT_FRACTIONAL_PADDING * extent
             self._cell_layout, order = cell_layout.CellLayout.from_positions(pos, lo, hi, nside or config.DEFAULT_CELLS_NSIDE)
-            self._particle_order = order[self._cell_layout.randomize_within_cells()]
+            self._host_order = order[self._cell_layout.randomize_within_cells()]
         else:
-            self._particle_order = np.arange(n)
-        self._pos = pos.astype(np.float32)[self._particle_order]
-        self._smooth = np.asarray(smooth).astype(np.float32)[self._particle_order]
-        self._mass = np.asarray(mass).astype(np.float32)[self._particle_order]
-        self._rgb = None if rgb is None else np.asarray(rgb, dtype=np.float32)[self._particle_order]
+            self._host_order = np.arange(n)
+        self._pos = pos.astype(np.float32)[self._host_order]
+        self._smooth = np.asarray(smooth).astype(np.float32)[self._host_order]
+        self._mass = np.asarray(mass).astype(np.float32)[self._host_order]
+        self._rgb = None if rgb is None else np.asarray(rgb, dtype=np.float32)[self._host_order]
+
+    def _init_on_device(self, pos, smooth, mass, rgb, lo, hi, extent, nside):
+        """The reference's load-time pipeline (loader.py:84-98: pad the bounding cube, bucket into cells, shuffle inside
+        cells, reorder every array) with all O(N) work on the GPU: one upload of the raw arrays, the K4 counting sort with
+        the within-cell shuffle fused in, and one gather per column.  The columns stay on the device for ParticleBuffers;
+        the host getters download them on demand."""
+        import torch
+        dev = self._device.torch_device
+        lo = lo - config.CELL_LAYOUT_FRACTIONAL_PADDING * extent
+        hi = hi + config.CELL_LAYOUT_FRACTIONAL_PADDING * extent
+        if pos.dtype not in (np.float32, np.float64):
+            pos = pos.astype(np.float64)
+        pos_d = torch.from_numpy(np.ascontiguousarray(pos)).to(dev)
+        seed = int(np.random.randint(1, 2 ** 31 - 1))          # the reference shuffles with the unseeded global numpy stream
+        self._cell_layout, order = cell_layout.CellLayout.from_positions(pos_d, lo, hi, nside, shuffle_seed=seed)
+        self._order_dev = order
+        self._dev = {}
+        for k, name in enumerate("xyz"):
+            self._dev[name] = self._gather(pos_d, stride=3, offset=k)
+        del pos_d
+        self._dev["h"] = self._gather(self._to_device(smooth))
+        self._dev["m"] = self._gather(self._to_device(mass))
+        if rgb is not None:
+            rgb_d = self._to_device(np.asarray(rgb))
+            for k, name in enumerate("rgb"):
+                self._dev["rgb_" + name] = self._gather(rgb_d, stride=3, offset=k).nan_to_num_(0.0)      # loader.py:119
+        self._pos = self._smooth = self._mass = self._rgb = None      # host copies are made on demand
+        self._has_rgb = rgb is not None
+
+    def _to_device(self, array):
+        import torch
+        array = np.asarray(array)
+        if array.dtype not in (np.float32, np.float64):
+            array = array.astype(np.float32)
+        return torch.from_numpy(np.ascontiguousarray(array)).to(self._device.torch_device)
+
+    def _gather(self, src, stride=1, offset=0):
+        """float32 copy of src[order * stride + offset] on the device (tsplat_gather_f32)."""
+        import ctypes
+
+        import torch
+
+        from . import _native as N
+        n = self._order_dev.numel()
+        out = torch.empty(n, dtype=torch.float32, device=src.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
+        N.check(N.lib().tsplat_gather_f32(src.device.index, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(src.data_ptr()),
+                                          src.element_size(), stride, offset, ctypes.c_void_p(self._order_dev.data_ptr()), n,
+                                          stream))
+        return out
+
+    @property
+    def _particle_order(self):
+        if self._order_dev is not None:
+            if getattr(self, "_host_order", None) is None:
+                self._host_order = self._order_dev.cpu().numpy()
+            return self._host_order
+        return self._host_order
+
+    def device_columns(self, names):
+        """Device-resident float32 columns ('x','y','z','h','m','rgb_r','rgb_g','rgb_b') for ParticleBuffers, or None when
+        the loader keeps its data on the host."""
+        if self._dev is None or any(k not in self._dev for k in names):
+            return None
+        return [self._dev[k] for k in names]
+
+    def device_quantity(self, name):
+        """A named quantity reordered on the device (None on the host path)."""
+        if self._dev is None:
+            return None
+        q = np.asarray(self._quantities[name])
+        if q.ndim == 2:
+            q = q[:, 0]
+        return self._gather(self._to_device(q))
 
     def __len__(self):
-        return len(self._pos)
+        return len(self._pos) if self._dev is None else int(self._dev["x"].numel())
+
+    def _keep_particles(self, indices):
+        if self._dev is not None:
+            import torch
+            idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(self._order_dev.device)
+            self._dev = {k: v[idx].contiguous() for k, v in self._dev.items()}
+            self._order_dev = self._order_dev[idx].contiguous()
+            self._host_order = None
+            return
+        self._pos, self._smooth, self._mass = self._pos[indices], self._smooth[indices], self._mass[indices]
+        if self._rgb is not None:
+            self._rgb = self._rgb[indices]
+        self._host_order = self._host_order[indices]
+
+    def _host(self, *names):
+        cols = [self._dev[k].cpu().numpy() for k in names]
+        return cols[0] if len(cols) == 1 else np.stack(cols, axis=1)
 
     def get_positions(self):
-        return self._pos
+        return self._pos if self._dev is None else self._host("x", "y", "z")
 
     def get_smooth(self):
-        return self._smooth
+        return self._smooth if self._dev is None else self._host("h")
 
     def get_mass(self):
-        return self._mass
+        return self._mass if self._dev is None else self._host("m")
 
     def get_named_quantity(self, name):
         q = np.asarray(self._quantities[name])
@@ -208,9 +316,12 @@ class ArrayDataLoader(AbstractDataLoader):
         return r"density / $M_{\odot} / \mathrm{kpc}^2$" if quantity_name is None else str(quantity_name)
 
     def get_rgb_masses(self):
-        if self._rgb is None:
+        if self._dev is not None and self._has_rgb:
+            rgb = self._host("rgb_r", "rgb_g", "rgb_b")
+        elif self._dev is None and self._rgb is not None:
+            rgb = self._rgb.copy()
+        else:
             raise ValueError("this snapshot has no rgb (band luminosity) arrays")
-        rgb = self._rgb.copy()
         rgb[np.isnan(rgb)] = 0.0
         return rgb
 

@@ -55,21 +55,46 @@ class ParticleBuffers:
             out.append(tuple(self._device.upload(c[a:b]) for c in columns))
         return out
 
+    def _device_columns(self, names):
+        """Columns a loader already holds on the device (ArrayDataLoader with the GPU cell layout): split into the
+        physical buffers as views, no host round trip.  None when the loader keeps its data on the host."""
+        getter = getattr(self._loader, "device_columns", None)
+        cols = getter(names) if getter is not None else None
+        if cols is None:
+            return None
+        return self._split_device_columns(cols)
+
+    def _split_device_columns(self, cols):
+        out = []
+        for k in range(self._split_buffers.num_buffers):
+            a, b = self._split_buffers.buffer_range(k)
+            out.append(tuple(c[a:b] for c in cols))
+        return out
+
     def get_pos_smooth_buffers(self):
         """Per buffer: (x, y, z, h) float32 tensors (the reference's 'pos_smooth' vertex buffer, :84-91)."""
         if not hasattr(self, "_pos_smooth_buffers"):
             logger.info("Creating position+smoothing buffer")
-            data = self._loader.get_pos_smooth().astype(np.float32)
-            self._pos_smooth_buffers = self._upload_columns([data[:, 0], data[:, 1], data[:, 2], data[:, 3]])
+            self._pos_smooth_buffers = self._device_columns(["x", "y", "z", "h"])
+            if self._pos_smooth_buffers is None:
+                data = self._loader.get_pos_smooth().astype(np.float32)
+                self._pos_smooth_buffers = self._upload_columns([data[:, 0], data[:, 1], data[:, 2], data[:, 3]])
         return self._pos_smooth_buffers
 
     def get_mass_and_quantity_buffers(self):
         """Per buffer: (m, q) -- q is None for a plain density render (:93-102)."""
         if self._quantity_buffer_is_for_name != self.quantity_name:
-            cols = [np.asarray(self._loader.get_mass(), dtype=np.float32)]
-            if self.quantity_name is not None:
-                cols.append(np.asarray(self._loader.get_named_quantity(self.quantity_name), dtype=np.float32))
-            bufs = self._upload_columns(cols)
+            mass_dev = self._device_columns(["m"])
+            if mass_dev is not None:
+                cols = [self._loader.device_columns(["m"])[0]]
+                if self.quantity_name is not None:
+                    cols.append(self._loader.device_quantity(self.quantity_name))
+                bufs = self._split_device_columns(cols)
+            else:
+                cols = [np.asarray(self._loader.get_mass(), dtype=np.float32)]
+                if self.quantity_name is not None:
+                    cols.append(np.asarray(self._loader.get_named_quantity(self.quantity_name), dtype=np.float32))
+                bufs = self._upload_columns(cols)
             self._mass_and_quantity_buffers = [b if len(b) == 2 else (b[0], None) for b in bufs]
             self._quantity_buffer_is_for_name = self.quantity_name
         return self._mass_and_quantity_buffers
@@ -78,8 +103,10 @@ class ParticleBuffers:
         """Per buffer: (r, g, b) (:104-111)."""
         if not hasattr(self, "_rgb_masses_buffers"):
             logger.info("Creating rgb buffer")
-            rgb = np.asarray(self._loader.get_rgb_masses(), dtype=np.float32)
-            self._rgb_masses_buffers = self._upload_columns([rgb[:, 0], rgb[:, 1], rgb[:, 2]])
+            self._rgb_masses_buffers = self._device_columns(["rgb_r", "rgb_g", "rgb_b"])
+            if self._rgb_masses_buffers is None:
+                rgb = np.asarray(self._loader.get_rgb_masses(), dtype=np.float32)
+                self._rgb_masses_buffers = self._upload_columns([rgb[:, 0], rgb[:, 1], rgb[:, 2]])
         return self._rgb_masses_buffers
 
     def specify_vertex_buffer_assignment(self, buffer_names):

@@ -42,7 +42,7 @@ class SPH:
                                ("boxsize_by_2_clipspace", np.float32, (1,)),
                                ("density_cut", np.float32, (1,))]
 
-    def __init__(self, visualizer, render_resolution, wrapping=False, share_render_progression=None):
+    def __init__(self, visualizer, render_resolution, wrapping=False, share_render_progression=None, exchange_cache=None):
         logger.info(f"Initializing {self.__class__} with resolution {render_resolution}")
         self._visualizer = visualizer
         self._render_resolution = render_resolution
@@ -57,6 +57,12 @@ class SPH:
             self._render_progression = visualizer.data_loader.get_render_progression()
         self._images = {}
         self._last_mode = None
+        # multi-GPU (no reference counterpart: topsy is single-device): under torchrun every rank holds a stripe of the
+        # particles (distributed.shard_loader); the renderer splats into a partial image and all-reduces it over NVLink
+        # after every frame, so that everything downstream (get_image, colormap, autorange) sees the full image.
+        from . import distributed
+        self._shard_rank, self._shard_world = distributed.shard_context()
+        self._exchanges = {} if exchange_cache is None else exchange_cache
 
         self.scale = config.DEFAULT_SCALE
         self.min_pixels = 0.0       # kept for API compatibility: like in the reference these have no effect
@@ -75,13 +81,24 @@ class SPH:
         Visualizer at the same resolution never clobbers this one's progressive state."""
         import torch
         channels = N.MODE_CHANNELS[mode]
+        if self._shard_world > 1:
+            return self._exchange_for(channels).partial
         if channels not in self._images:
             self._images[channels] = torch.zeros((self._render_resolution, self._render_resolution, channels),
                                                  dtype=torch.float32, device=self._device.torch_device)
         return self._images[channels]
 
+    def _exchange_for(self, channels):
+        if channels not in self._exchanges:
+            from . import distributed
+            self._exchanges[channels] = distributed.ImageExchange(self._engine, self._render_resolution, channels)
+        return self._exchanges[channels]
+
     def _current_image(self):
-        return self._image_for_mode(self._last_mode if self._last_mode is not None else self._mode())
+        mode = self._last_mode if self._last_mode is not None else self._mode()
+        if self._shard_world > 1:
+            return self._exchange_for(N.MODE_CHANNELS[mode]).reduced      # the all-reduced image, identical on every rank
+        return self._image_for_mode(mode)
 
     def get_output_texture(self) -> Texture:
         return self._render_texture
@@ -141,11 +158,24 @@ class SPH:
         self._render_timer.end_frame()
 
         self.last_render_mass_scale = self._render_progression.end_frame_get_scalefactor()
+        if self._shard_world > 1:
+            # reduced = sum over ranks of (rank's mass scale) * (rank's partial image): already an estimate of the full
+            # image, so nothing is left to rescale afterwards
+            self._exchange_for(N.MODE_CHANNELS[mode]).allreduce(self.last_render_mass_scale, zmax=(mode == N.MODE_SURFACE))
+            self.last_render_mass_scale = 1.0
         self.last_render_fps = 1.0 / max(self._render_timer.running_mean_duration, 1e-9)
         self.has_rendered = True
 
     def needs_refine(self):
-        return self._render_progression.needs_refine()
+        local = self._render_progression.needs_refine()
+        if self._shard_world > 1:
+            # frames are collective (every render ends in the image all-reduce): all ranks refine until the last is done
+            import torch
+            import torch.distributed as dist
+            flag = torch.tensor([1 if local else 0], dtype=torch.int32, device=self._device.torch_device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            return bool(int(flag.item()))
+        return local
 
     # -- readback -------------------------------------------------------------------------------------------
     def _get_image_unscaled(self):
@@ -164,8 +194,11 @@ class SPH:
         return self._get_image_unscaled() * self.last_render_mass_scale
 
     def _get_depth_renderer(self):
+        if not hasattr(self, "_depth_exchanges"):
+            self._depth_exchanges = {}          # the throw-away depth renderers share one set of symmetric images
         renderer = DepthSPH(self._visualizer, self._render_resolution, wrapping=self._wrapping,
-                            share_render_progression=copy.copy(self._render_progression))
+                            share_render_progression=copy.copy(self._render_progression),
+                            exchange_cache=self._depth_exchanges)
         renderer.rotation_matrix = self.rotation_matrix
         renderer.position_offset = self.position_offset
         renderer.scale = self.scale
@@ -219,8 +252,8 @@ class DepthSPHWithOcclusion(SPH):
     _nchannels_output = 2
     _rho_percentiles_num_samples = 101      # the density cut is tabulated at every percentile from 0 to 100
 
-    def __init__(self, visualizer, render_resolution, wrapping=False, share_render_progression=None):
-        super().__init__(visualizer, render_resolution, wrapping, share_render_progression)
+    def __init__(self, visualizer, render_resolution, wrapping=False, share_render_progression=None, exchange_cache=None):
+        super().__init__(visualizer, render_resolution, wrapping, share_render_progression, exchange_cache)
         mass = self._visualizer.data_loader.get_mass()
         smooth = self._visualizer.data_loader.get_smooth()
         rho = mass / smooth ** 3

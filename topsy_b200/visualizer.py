@@ -84,6 +84,11 @@ class VisualizerBase:
 
     def _initialize_data_loader_and_buffers(self, data_loader_class, data_loader_args, data_loader_kwargs):
         self.data_loader = data_loader_class(self.device, *data_loader_args, **data_loader_kwargs)
+        # multi-GPU: under torchrun every rank keeps its per-cell stripe of the snapshot (no reference counterpart; the
+        # wiring extended here is visualizer.py:75-80 loader -> ParticleBuffers)
+        from . import distributed
+        rank, world = distributed.shard_context()
+        distributed.shard_loader(self.data_loader, rank, world)
         regions = self.data_loader.get_render_progression().get_max_particle_regions_per_block()
         self.particle_buffers = particle_buffers.ParticleBuffers(self.data_loader, self.device, regions)
         self.periodicity_scale = self.data_loader.get_periodicity_scale()
