@@ -505,12 +505,17 @@ def run_ours(args):
         d2h = host_out[0].numel() * host_out[0].element_size()
 
         copy_stream = torch.cuda.Stream(device=dev)
+        d2h_stream = torch.cuda.Stream(device=dev)
         h2d_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        rendered = torch.cuda.Event()                  # the splat of the previous frame has read the device arrays
+        downloaded = [None, None]                      # D2H of frame f (host_out[f & 1]) has finished
 
         def e2e_frame(i, timed=False):
-            # the uploads of EXPORT block b+1 overlap the splat of block b: copies on their own stream, one event per block
+            # uploads of EXPORT block b+1 overlap the splat of block b (copies on their own stream, one event per block);
+            # the D2H of frame f runs on a third stream and overlaps the uploads of frame f+1 (PCIe is full duplex)
             main = torch.cuda.current_stream(dev)
-            copy_stream.wait_stream(main)                 # the previous frame has finished reading the device arrays
+            if i > 0:
+                copy_stream.wait_event(rendered)
             ready = []
             with torch.cuda.stream(copy_stream):
                 if timed:
@@ -526,20 +531,33 @@ def run_ours(args):
             for b, (s, l) in enumerate(blocks):
                 main.wait_event(ready[b])
                 eng.render(mode, [s], [l], clear=(b == 0), image=sharded.image)
+            rendered.record(main)
+            if downloaded[(i - 1) & 1] is not None:
+                main.wait_event(downloaded[(i - 1) & 1])          # `out` is free again
             sharded.present(params, lut)
             if rank == 0:
-                eng.download(host_out[i & 1], out)
-            eng.synchronize()
+                presented = torch.cuda.Event()
+                presented.record(main)
+                if downloaded[i & 1] is not None:
+                    downloaded[i & 1].synchronize()                 # host_out[i & 1] was consumed two frames ago
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(presented)
+                    eng.download(host_out[i & 1], out)
+                    ev = torch.cuda.Event()
+                    ev.record(d2h_stream)
+                    downloaded[i & 1] = ev
 
         n_e2e = max(2, min(args.steps, 5))
         e2e_frame(0)
+        torch.cuda.synchronize()
+        downloaded[0] = downloaded[1] = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(n_e2e):
             e2e_frame(i, timed=(i == n_e2e - 1))
-        torch.cuda.synchronize()
+        torch.cuda.synchronize()                       # every frame's RGBA image is in host memory
         dt = (time.perf_counter() - t0) / n_e2e
         h2d_gbs = h2d / (h2d_ev[0].elapsed_time(h2d_ev[1]) * 1e-3) / 1e9
         tt = torch.tensor([dt, -h2d_gbs], device=dev, dtype=torch.float64)
@@ -551,7 +569,7 @@ def run_ours(args):
                "host_binding": numa,
                "path": "pinned host SoA (allocated after binding the rank to its GPU's NUMA node) -> tsplat_memcpy_h2d per EXPORT "
                        "block on a copy stream, overlapped with tsplat_render of the previous block -> [image sum +] "
-                       "tsplat_colormap -> tsplat_memcpy_d2h on rank 0"}
+                       "tsplat_colormap -> tsplat_memcpy_d2h of every frame on rank 0 (third stream, overlapping the next frame's uploads)"}
         del host
 
     if rank == 0:
@@ -591,7 +609,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         if red_peak:
-            lanes = st["direct_vector_reds"] / max(args.steps + args.warmup + (2 if world > 1 else 1), 1)
+            lanes = st["direct_vector_reds"]               # the counters restart with every frame's first (clearing) block
             line["atomic_roofline"] = {
                 "bound": "vector RED lane rate for lanes grouped in 2x2 pixel quads like this workload's footprints, read from "
                          "profiles/r02/red_peaks.json (measured on B200 by profiles/microbench/red_patterns_bench.cu and "

@@ -153,6 +153,11 @@ int tsplat_allreduce_image(tsplat_ctx *ctx, const float *const *peer_images, flo
                            const float *const *peer_scale, int n_peers, int channels, int row0, int nrows, int op,
                            void *stream);
 
+/* A process that drives several GPUs itself (no torchrun) lets `device_ordinal`'s kernels load / store `peer_ordinal`'s
+ * memory (cudaDeviceEnablePeerAccess); already-enabled is not an error.  Multi-process runs get their peer mappings from
+ * PyTorch symmetric memory instead. */
+int tsplat_enable_peer_access(int device_ordinal, int peer_ordinal);
+
 /* Replaces PeriodicSPH's accumulation pass (periodic_sph.py:59-88, overlay.py, shaders/overlay.wgsl): dst (R x R x
  * channels, device) = sum over n <= 128 replicas of weights[i] * src sampled bilinearly at the pixel shifted by the
  * clip-space offset (offsets_xy[2i], offsets_xy[2i+1]); a replica contributes only inside its own [-1,1]^2 + offset

@@ -1997,7 +1997,8 @@ extern "C" int tsplat_bilateral_filter(tsplat_ctx *c, const float *in, float *ou
     a.kernel_size = kernel_size;
     dim3 grid((width + 31) / 32, (height + 7) / 8);
     const size_t smem = tsplat_surface::bilateral_smem_bytes(kernel_size / 2);
-    if (smem <= 200 * 1024) {
+    static const bool force_direct = getenv("TSPLAT_BILATERAL_DIRECT") != nullptr;      // A/B timing of the round-1 kernel
+    if (smem <= 200 * 1024 && !force_direct) {
         if (smem > 48 * 1024 && smem > c->bilateral_smem_set) {
             CUDA_TRY(cudaFuncSetAttribute(tsplat_surface::k_bilateral_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             c->bilateral_smem_set = smem;
@@ -2060,6 +2061,18 @@ extern "C" int tsplat_reduce_colormap(tsplat_ctx *c, const float *const *peer_im
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_enable_peer_access(int device_ordinal, int peer_ordinal)
+{
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    int can = 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, device_ordinal, peer_ordinal));
+    if (!can) return set_err(TSPLAT_ERR_STATE, "device %d cannot access device %d", device_ordinal, peer_ordinal);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_ordinal, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return TSPLAT_OK; }
+    CUDA_TRY(e);
     return TSPLAT_OK;
 }
 

@@ -126,7 +126,7 @@ __device__ __forceinline__ float kp_get(const float4 &v, int e) { return e == 0 
 // Level-3 LUT fetch for a pixel centre the footprint COVERS (px0 <= fx < px1, py0 <= fy < py1).  Same operations as
 // sample_lut8(): u = (fx - px0) * inv, floor(u * 8) -- with inv8 = inv * 8 (an exact scaling, so (fx - px0) * inv8 ==
 // ((fx - px0) * inv) * 8 bit for bit); covered centres have u, v >= 0, so only the upper clamp can ever act.
-__device__ __forceinline__ float kp_lut8_covered(const float *__restrict__ s_lut8, float inv8, float px0, float py1, float fx, float fy)
+__device__ __forceinline__ float kp_lut8_covered(const float (&s_lut8)[64], float inv8, float px0, float py1, float fx, float fy)
 {
     const int iu = min(__float2int_rd((fx - px0) * inv8), 7);
     const int iv = min(__float2int_rd((py1 - fy) * inv8), 7);
@@ -136,7 +136,7 @@ __device__ __forceinline__ float kp_lut8_covered(const float *__restrict__ s_lut
 // One cell (CELL_W horizontally adjacent pixels = one 128-bit RED: RGB 1, WEIGHTED / DEPTH 2, DENSITY 4) of pixel row k.
 // [j0, j1] = the record's covered pixel columns, cj = cell column; row k is covered.
 template <int MODE, int CELL_W>
-__device__ __forceinline__ void kp_emit_cell(const ProjectArgs &a, const float *__restrict__ s_lut8, uint64_t pol_image,
+__device__ __forceinline__ void kp_emit_cell(const ProjectArgs &a, const float (&s_lut8)[64], uint64_t pol_image,
                                              float px0, float py1, float inv8, float v0, float v1, float v2, unsigned j0,
                                              unsigned j1, unsigned cj, unsigned k)
 {
