@@ -1311,25 +1311,37 @@ struct ReduceArgs {
     float *sum_out;         // full R x R x C fp32 image receiving the reduced slab, or nullptr
 };
 
+// Each thread owns 4 consecutive floats of the slab (4 / 2 / 1 pixels for 1 / 2 / 4 channels): one 128-bit load per peer,
+// all of them issued before the first add so that the NVLink round trips overlap (a 4-byte load per thread and peer, one
+// after the other, reached 318 GB/s of a 770 GB/s link: profiles/r02/k6_peer_timing_v1.json).
 __global__ void __launch_bounds__(256) k_reduce_colormap(const ReduceArgs a)
 {
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-    const int oy = a.row0 + blockIdx.y;
-    if (ox >= a.res || blockIdx.y >= (unsigned)a.nrows) return;
+    const int64_t first = (int64_t)a.row0 * a.res * a.channels, count = (int64_t)a.nrows * a.res * a.channels;
+    const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= count) return;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; r < a.n_peers; ++r) {
-        float t[4];
-        load_pixel(a.peer[r], a.res, a.channels, ox, oy, t);
+    if (i4 + 4 <= count && ((first + i4) & 3) == 0) {
+        float4 t[MAX_PEERS];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] += t[c];
+        for (int r = 0; r < MAX_PEERS; ++r)
+            if (r < a.n_peers) t[r] = __ldg(reinterpret_cast<const float4 *>(a.peer[r] + first + i4));
+#pragma unroll
+        for (int r = 0; r < MAX_PEERS; ++r)
+            if (r < a.n_peers) { v[0] += t[r].x; v[1] += t[r].y; v[2] += t[r].z; v[3] += t[r].w; }
+    } else {
+        for (int e = 0; e < 4 && i4 + e < count; ++e)
+            for (int r = 0; r < a.n_peers; ++r) v[e] += a.peer[r][first + i4 + e];
     }
-    const size_t pix = (size_t)oy * a.res + ox;
-    if (a.sum_out) {
-        if (a.channels == 1) a.sum_out[pix] = v[0];
-        else if (a.channels == 2) reinterpret_cast<float2 *>(a.sum_out)[pix] = make_float2(v[0], v[1]);
-        else reinterpret_cast<float4 *>(a.sum_out)[pix] = make_float4(v[0], v[1], v[2], v[3]);
+    const int n_valid = (int)min((int64_t)4, count - i4);
+    if (a.sum_out)
+        for (int e = 0; e < n_valid; ++e) a.sum_out[first + i4 + e] = v[e];
+    if (a.out) {
+        const int C = a.channels;
+        for (int e = 0; e + C <= n_valid; e += C) {
+            float px[4] = {v[e], C > 1 ? v[e + 1] : 0.f, C > 2 ? v[e + 2] : 0.f, C > 2 ? v[e + 3] : 0.f};
+            store_rgba(a.out, (size_t)((first + i4 + e) / C), a.out_fmt, colormap_value(px, a.p, a.lut, a.lut_w, a.lut_h));
+        }
     }
-    if (a.out) store_rgba(a.out, pix, a.out_fmt, colormap_value(v, a.p, a.lut, a.lut_w, a.lut_h));
 }
 
 // K6b: image all-reduce over NVLink peer memory for the drop-in classes: every rank reduces its slab of rows over all
@@ -2056,8 +2068,8 @@ extern "C" int tsplat_reduce_colormap(tsplat_ctx *c, const float *const *peer_im
     a.n_peers = n_peers; a.res = c->R; a.channels = channels; a.row0 = row0; a.nrows = nrows;
     if (params) a.p = *params;
     a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_fmt = out_fmt; a.sum_out = sum_out;
-    dim3 grid((c->R + 255) / 256, nrows);
-    k_reduce_colormap<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    const int64_t quads = ((int64_t)nrows * c->R * channels + 3) / 4;
+    k_reduce_colormap<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());
