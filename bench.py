@@ -435,6 +435,21 @@ def run_ours(args):
         torch.cuda.empty_cache()
         dist.barrier()
 
+    # the fused reduce+colormap kernel alone (between the two barriers): its NVLink traffic is (G-1)/G of the image in, and
+    # the RGBA slab out to rank 0
+    reduce_kernel = None
+    if world > 1 and sharded.method == "p2p":
+        sharded.kernel_events = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        frame(); frame()
+        torch.cuda.synchronize()
+        k_ms = torch.tensor([sharded.kernel_events[0].elapsed_time(sharded.kernel_events[1])], device=dev, dtype=torch.float64)
+        dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
+        sharded.kernel_events = None
+        link_bytes = (world - 1) / world * R * R * C * 4
+        reduce_kernel = {"kernel": "k_reduce_colormap", "ms_max_over_ranks": float(k_ms[0]), "nvlink_bytes_in_per_rank": link_bytes,
+                         "nvlink_GBs_in_per_rank": link_bytes / (float(k_ms[0]) * 1e-3) / 1e9,
+                         "frac_of_measured_peer_copy_770GBs": link_bytes / (float(k_ms[0]) * 1e-3) / 1e9 / 770.0}
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -625,6 +640,8 @@ def run_ours(args):
                                          "Gparticles_per_s": n / (subpixel["splat_ms"] * 1e-3) / 1e9}
         if parity is not None:
             line["parity"] = parity
+        if reduce_kernel is not None:
+            line["reduce_kernel"] = reduce_kernel
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:

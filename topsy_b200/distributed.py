@@ -209,6 +209,7 @@ class ShardedSplat:
         if reduce == "auto":
             self.method = "p2p" if self.world > 1 else "local"
         self._hdl = self._out_hdl = None
+        self.kernel_events = None          # optional (start, end) CUDA events around the fused kernel alone (bench.py)
         shape = (resolution, resolution, channels)
         if self.method == "p2p" and self.world > 1:
             try:
@@ -248,12 +249,16 @@ class ShardedSplat:
         if self.method == "p2p":
             import torch
             self._hdl.barrier()                                   # every rank's partial image is complete and visible
+            if self.kernel_events is not None:
+                self.kernel_events[0].record()
             row0, nrows = row_slab(self.resolution, self.rank, self.world)
             lw, lh = (0, 0) if lut is None else ((lut.shape[0], 1) if lut.dim() == 2 else (lut.shape[1], lut.shape[0]))
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             N.check(eng.lib.tsplat_reduce_colormap(eng._ctx, self._peer_ptrs, self.world, self.channels, row0, nrows,
                                                    ctypes.byref(params), None if lut is None else ctypes.c_void_p(lut.data_ptr()),
                                                    lw, lh, ctypes.c_void_p(self._out0), self._fmt, None, stream))
+            if self.kernel_events is not None:
+                self.kernel_events[1].record()
             self._out_hdl.barrier()                               # rank 0's output is complete; images may be cleared
             return self.out
         # nccl baseline: reduce a copy so that the partial image stays valid (progressive REFINE frames keep adding to it)
