@@ -97,12 +97,13 @@ def visualizer_check(rank, world):
     # the unsharded reference runs the same kind of sequence: interactive frames draw only the cells selected by
     # select_sphere(-offset, 1.2 scale) (sph.py:313), an EXPORT frame draws everything (reference quirk)
     assert interactive_sequence(ref_vis, 47000) > 1
-    assert interactive_sequence(vis, 20000 + 7000 * rank) > 1
+    # (never the whole stripe in one block: a block that is the whole set skips the cell selection, progressive_render.py:197-198)
+    assert interactive_sequence(vis, len(vis.data_loader) // 4 + 300 * rank) > 1
     want, got = ref_vis._sph.get_image()[..., 0].astype(np.float64), vis._sph.get_image()[..., 0].astype(np.float64)
     big = want > 1e-6 * want.max()
     rel = np.abs(got[big] - want[big]) / want[big]
     assert rel.max() <= 1e-4, ("progressive", rel.max())
-    # and a partially refined state: after ONE frame the ranks have drawn different fractions (20 % and 27 %) of their
+    # and a partially refined state: after ONE frame the ranks have drawn different fractions (25 % + 300 rank) of their
     # stripes; the mass-scale weighted reduce must still estimate the full image (statistically: mean ratio ~ 1)
     vis.invalidate(DrawReason.CHANGE)
     vis.render_sph(DrawReason.CHANGE)

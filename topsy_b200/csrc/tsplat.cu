@@ -1337,9 +1337,24 @@ __global__ void __launch_bounds__(256) k_reduce_colormap(const ReduceArgs a)
         for (int e = 0; e < n_valid; ++e) a.sum_out[first + i4 + e] = v[e];
     if (a.out) {
         const int C = a.channels;
-        for (int e = 0; e + C <= n_valid; e += C) {
-            float px[4] = {v[e], C > 1 ? v[e + 1] : 0.f, C > 2 ? v[e + 2] : 0.f, C > 2 ? v[e + 3] : 0.f};
-            store_rgba(a.out, (size_t)((first + i4 + e) / C), a.out_fmt, colormap_value(px, a.p, a.lut, a.lut_w, a.lut_h));
+        if (a.out_fmt == TSPLAT_FMT_RGBA8 && n_valid == 4 && C < 4) {
+            // 4 (or 2) pixels of this thread leave as ONE 16 (8) byte store: the output usually lives on another GPU, and
+            // 4-byte stores at a 16-byte stride cross NVLink as partial sectors (c5 on 8 GPUs: 0.48 ms instead of 0.14)
+            unsigned packed[4];
+            for (int e = 0; e < 4; e += C) {
+                float px[4] = {v[e], C > 1 ? v[e + 1] : 0.f, 0.f, 0.f};
+                const float4 rgba = colormap_value(px, a.p, a.lut, a.lut_w, a.lut_h);
+                packed[e / C] = (unsigned)__float2int_rn(__saturatef(rgba.x) * 255.0f) | ((unsigned)__float2int_rn(__saturatef(rgba.y) * 255.0f) << 8) |
+                                ((unsigned)__float2int_rn(__saturatef(rgba.z) * 255.0f) << 16) | ((unsigned)__float2int_rn(__saturatef(rgba.w) * 255.0f) << 24);
+            }
+            unsigned *dst = reinterpret_cast<unsigned *>(a.out) + (first + i4) / C;
+            if (C == 1) *reinterpret_cast<uint4 *>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            else *reinterpret_cast<uint2 *>(dst) = make_uint2(packed[0], packed[1]);
+        } else {
+            for (int e = 0; e + C <= n_valid; e += C) {
+                float px[4] = {v[e], C > 1 ? v[e + 1] : 0.f, C > 2 ? v[e + 2] : 0.f, C > 2 ? v[e + 3] : 0.f};
+                store_rgba(a.out, (size_t)((first + i4 + e) / C), a.out_fmt, colormap_value(px, a.p, a.lut, a.lut_w, a.lut_h));
+            }
         }
     }
 }
