@@ -1314,6 +1314,7 @@ struct ReduceArgs {
 // Each thread owns 4 consecutive floats of the slab (4 / 2 / 1 pixels for 1 / 2 / 4 channels): one 128-bit load per peer,
 // all of them issued before the first add so that the NVLink round trips overlap (a 4-byte load per thread and peer, one
 // after the other, reached 318 GB/s of a 770 GB/s link: profiles/r02/k6_peer_timing_v1.json).
+template <int NP>      // peers known at compile time (2..8; 16 = any number, predicated): all NP loads are issued back to back
 __global__ void __launch_bounds__(256) k_reduce_colormap(const ReduceArgs a)
 {
     const int64_t first = (int64_t)a.row0 * a.res * a.channels, count = (int64_t)a.nrows * a.res * a.channels;
@@ -1321,13 +1322,13 @@ __global__ void __launch_bounds__(256) k_reduce_colormap(const ReduceArgs a)
     if (i4 >= count) return;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (i4 + 4 <= count && ((first + i4) & 3) == 0) {
-        float4 t[MAX_PEERS];
+        float4 t[NP];
 #pragma unroll
-        for (int r = 0; r < MAX_PEERS; ++r)
-            if (r < a.n_peers) t[r] = __ldg(reinterpret_cast<const float4 *>(a.peer[r] + first + i4));
+        for (int r = 0; r < NP; ++r)
+            if (NP < MAX_PEERS || r < a.n_peers) t[r] = __ldg(reinterpret_cast<const float4 *>(a.peer[r] + first + i4));
 #pragma unroll
-        for (int r = 0; r < MAX_PEERS; ++r)
-            if (r < a.n_peers) { v[0] += t[r].x; v[1] += t[r].y; v[2] += t[r].z; v[3] += t[r].w; }
+        for (int r = 0; r < NP; ++r)
+            if (NP < MAX_PEERS || r < a.n_peers) { v[0] += t[r].x; v[1] += t[r].y; v[2] += t[r].z; v[3] += t[r].w; }
     } else {
         for (int e = 0; e < 4 && i4 + e < count; ++e)
             for (int r = 0; r < a.n_peers; ++r) v[e] += a.peer[r][first + i4 + e];
@@ -1369,6 +1370,7 @@ struct AllReduceArgs {
     int64_t first, count;      // slab as a range of floats of the flattened (R, R, C) image
 };
 
+template <int NP>
 __global__ void __launch_bounds__(256) k_allreduce_image(const AllReduceArgs a)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1389,15 +1391,16 @@ __global__ void __launch_bounds__(256) k_allreduce_image(const AllReduceArgs a)
         const int64_t n4 = a.count >> 2;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 t[NP];
 #pragma unroll
-            for (int r = 0; r < MAX_PEERS; ++r)
-                if (r < a.n_peers) {
-                    const float4 t = reinterpret_cast<const float4 *>(a.peer[r] + a.first)[i];
-                    v.x += w[r] * t.x; v.y += w[r] * t.y; v.z += w[r] * t.z; v.w += w[r] * t.w;
-                }
+            for (int r = 0; r < NP; ++r)
+                if (NP < MAX_PEERS || r < a.n_peers) t[r] = __ldg(reinterpret_cast<const float4 *>(a.peer[r] + a.first) + i);
 #pragma unroll
-            for (int r = 0; r < MAX_PEERS; ++r)
-                if (r < a.n_peers) reinterpret_cast<float4 *>(a.out[r] + a.first)[i] = v;
+            for (int r = 0; r < NP; ++r)
+                if (NP < MAX_PEERS || r < a.n_peers) { v.x += w[r] * t[r].x; v.y += w[r] * t[r].y; v.z += w[r] * t[r].z; v.w += w[r] * t[r].w; }
+#pragma unroll
+            for (int r = 0; r < NP; ++r)
+                if (NP < MAX_PEERS || r < a.n_peers) reinterpret_cast<float4 *>(a.out[r] + a.first)[i] = v;
         }
     } else {
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += stride) {
@@ -2084,7 +2087,19 @@ extern "C" int tsplat_reduce_colormap(tsplat_ctx *c, const float *const *peer_im
     if (params) a.p = *params;
     a.lut = lut; a.lut_w = lut_w; a.lut_h = lut_h; a.out = out; a.out_fmt = out_fmt; a.sum_out = sum_out;
     const int64_t quads = ((int64_t)nrows * c->R * channels + 3) / 4;
-    k_reduce_colormap<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    const unsigned rgrid = (unsigned)((quads + 255) / 256);
+    cudaStream_t rst = (cudaStream_t)stream;
+    switch (n_peers) {
+    case 1: k_reduce_colormap<1><<<rgrid, 256, 0, rst>>>(a); break;
+    case 2: k_reduce_colormap<2><<<rgrid, 256, 0, rst>>>(a); break;
+    case 3: k_reduce_colormap<3><<<rgrid, 256, 0, rst>>>(a); break;
+    case 4: k_reduce_colormap<4><<<rgrid, 256, 0, rst>>>(a); break;
+    case 5: k_reduce_colormap<5><<<rgrid, 256, 0, rst>>>(a); break;
+    case 6: k_reduce_colormap<6><<<rgrid, 256, 0, rst>>>(a); break;
+    case 7: k_reduce_colormap<7><<<rgrid, 256, 0, rst>>>(a); break;
+    case 8: k_reduce_colormap<8><<<rgrid, 256, 0, rst>>>(a); break;
+    default: k_reduce_colormap<MAX_PEERS><<<rgrid, 256, 0, rst>>>(a); break;
+    }
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());
@@ -2129,7 +2144,13 @@ extern "C" int tsplat_allreduce_image(tsplat_ctx *c, const float *const *peer_im
     int64_t blocks = (a.count / 4 + 255) / 256;
     if (blocks > (int64_t)c->sm_count * 8) blocks = (int64_t)c->sm_count * 8;
     if (blocks < 1) blocks = 1;
-    k_allreduce_image<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t ast = (cudaStream_t)stream;
+    switch (n_peers) {
+    case 2: k_allreduce_image<2><<<(unsigned)blocks, 256, 0, ast>>>(a); break;
+    case 4: k_allreduce_image<4><<<(unsigned)blocks, 256, 0, ast>>>(a); break;
+    case 8: k_allreduce_image<8><<<(unsigned)blocks, 256, 0, ast>>>(a); break;
+    default: k_allreduce_image<MAX_PEERS><<<(unsigned)blocks, 256, 0, ast>>>(a); break;
+    }
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());
