@@ -84,6 +84,14 @@ typedef struct {
     int64_t direct_vector_reds;     /* 128-bit (or narrower) REDs issued by the direct path since the last clear */
 } tsplat_stats;
 
+/* Live timing of the dominant kernel (K1, the project + direct-splat pass): with timing enabled every tsplat_render brackets
+ * its K1 launch with CUDA events on the caller's stream (a ring of TSPLAT_TIMING_SLOTS pairs); tsplat_kernel_timing
+ * synchronises those events and returns the number of K1 launches recorded since the last query and their summed
+ * duration.  For bench.py's roofline (achieved = algorithmic bytes per launch / this duration); off by default. */
+#define TSPLAT_TIMING_SLOTS 256
+int tsplat_enable_kernel_timing(tsplat_ctx *ctx, int enable);
+int tsplat_kernel_timing(tsplat_ctx *ctx, int64_t *n_launches, double *total_ms);
+
 const char *tsplat_last_error(void);
 int tsplat_abi_version(void);
 

@@ -80,6 +80,8 @@ _SIGNATURES = {
     "tsplat_allreduce_image": (_i32, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i32, _i32, _i32, _i32,
                                       _i32, _vp]),
     "tsplat_enable_peer_access": (_i32, [_i32, _i32]),
+    "tsplat_enable_kernel_timing": (_i32, [_vp, _i32]),
+    "tsplat_kernel_timing": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double)]),
     "tsplat_set_surface": (_i32, [_vp, _vp, _i32, _f]),
     "tsplat_bilateral_filter": (_i32, [_vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "tsplat_surface_shade": (_i32, [_vp, _vp, _i32, ctypes.POINTER(SurfaceParams), _vp, _i32, _vp, _i32, _i32, _i32, _vp]),

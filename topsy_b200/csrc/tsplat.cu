@@ -113,6 +113,11 @@ struct tsplat_ctx {
     bool bin_attr_set;
     bool gather_attr_set[4];
     size_t bilateral_smem_set;   // largest dynamic shared-memory size k_bilateral_filter has been opted into
+    // optional live timing of K1 (tsplat_enable_kernel_timing): ring of event pairs, [timing_read, timing_write) pending
+    bool timing;
+    cudaEvent_t t_begin[TSPLAT_TIMING_SLOTS], t_end[TSPLAT_TIMING_SLOTS];
+    bool timing_events_created;
+    int64_t timing_read, timing_write;
 };
 
 extern "C" const char *tsplat_last_error(void) { return g_err; }
@@ -1177,7 +1182,7 @@ __device__ __forceinline__ float4 colormap_value(const float v[4], const tsplat_
             float val = c3[c];
             if (p.log_scale) val = wgsl_log10(val);
             const float t = fmaxf((val - p.vmin) / (p.vmax - p.vmin), 0.0f);
-            c3[c] = powf(t, p.gamma);
+            c3[c] = p.gamma == 1.0f ? t : powf(t, p.gamma);      // pow(t, 1) == t: skip ~100 instructions per band in the default case
         }
         return make_float4(c3[0], c3[1], c3[2], 1.0f);
     }
@@ -1613,6 +1618,8 @@ extern "C" int tsplat_destroy(tsplat_ctx *c)
     cudaFree(c->d_counters);
     cudaFree(c->d_select);
     cudaFreeHost(c->h_select);
+    if (c->timing_events_created)
+        for (int i = 0; i < TSPLAT_TIMING_SLOTS; ++i) { cudaEventDestroy(c->t_begin[i]); cudaEventDestroy(c->t_end[i]); }
     for (int s = 0; s < RANGE_SLOTS; ++s) {
         cudaFreeHost(c->h_ranges[s]);
         cudaFree(c->d_ranges[s]);
@@ -1749,6 +1756,8 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
     if (blocks > 0) {
         // cell width of the vector REDs: as many pixels as fit 128 bits, if rows keep the cells aligned
         constexpr int CW = ModeTraits<MODE>::C == 1 ? 4 : ModeTraits<MODE>::C == 2 ? 2 : 1;
+        const bool timed = c->timing && c->timing_write - c->timing_read < TSPLAT_TIMING_SLOTS;
+        if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->timing_write % TSPLAT_TIMING_SLOTS], st));
         static const bool use_v1 = getenv("TSPLAT_K1_V1") != nullptr;       // round-1 kernel, kept for A/B timing only
         if (use_v1) {
             if (CW > 1 && (c->R % CW) == 0) k_project_splat<MODE, CW><<<(unsigned)blocks, threads, 0, st>>>(pa);
@@ -1765,6 +1774,7 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
                 k_project_stream<MODE, 1><<<(unsigned)(grid < max_grid ? grid : max_grid), KP_THREADS, 0, st>>>(pa);
             }
         }
+        if (timed) { CUDA_TRY(cudaEventRecord(c->t_end[c->timing_write % TSPLAT_TIMING_SLOTS], st)); c->timing_write++; }
         c->launches++;
     }
     if (pa.queue_cap > 0 && pa.small_call) {
@@ -2103,6 +2113,37 @@ extern "C" int tsplat_reduce_colormap(tsplat_ctx *c, const float *const *peer_im
     c->launches++;
     c->last_stream = (cudaStream_t)stream;
     CUDA_TRY(cudaGetLastError());
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_enable_kernel_timing(tsplat_ctx *c, int enable)
+{
+    if (!c) return set_err(TSPLAT_ERR_INVALID, "NULL context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (enable && !c->timing_events_created) {
+        for (int i = 0; i < TSPLAT_TIMING_SLOTS; ++i) {
+            CUDA_TRY(cudaEventCreate(&c->t_begin[i]));
+            CUDA_TRY(cudaEventCreate(&c->t_end[i]));
+        }
+        c->timing_events_created = true;
+    }
+    c->timing = enable != 0;
+    c->timing_read = c->timing_write = 0;
+    return TSPLAT_OK;
+}
+
+extern "C" int tsplat_kernel_timing(tsplat_ctx *c, int64_t *n_launches, double *total_ms)
+{
+    if (!c || !n_launches || !total_ms) return set_err(TSPLAT_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    *n_launches = 0; *total_ms = 0.0;
+    for (; c->timing_read < c->timing_write; ++c->timing_read) {
+        const int i = (int)(c->timing_read % TSPLAT_TIMING_SLOTS);
+        CUDA_TRY(cudaEventSynchronize(c->t_end[i]));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->t_begin[i], c->t_end[i]));
+        *total_ms += ms; ++*n_launches;
+    }
     return TSPLAT_OK;
 }
 

@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(KP_THREADS, 5) k_project_stream(const ProjectA
                             (unsigned)ny1 < (unsigned)KP_MAX_SPAN;
         const bool defer = covered && !direct;
         // stack A: one pixel row and all columns inside one cell
-        const bool one = ny1 == 0 && ((unsigned)j0 >> CELL_SHIFT) == ((unsigned)(jend - 1) >> CELL_SHIFT);
+        const bool one = CELL_W == 1 ? (nx1 | ny1) == 0
+                                     : (ny1 == 0 && ((unsigned)j0 >> CELL_SHIFT) == ((unsigned)(jend - 1) >> CELL_SHIFT));
         const bool to_a = direct && one, to_b = direct && !one;
         n_culled += (unsigned)(in && !p.keep);
         defer_mask |= (unsigned)defer << e;
@@ -328,7 +329,8 @@ __global__ void __launch_bounds__(KP_THREADS, 5) k_project_stream(const ProjectA
             const unsigned rank = (unsigned)__popc((to_a ? ma : mb) & lt_mask);
             const unsigned idx = to_a ? qa_count + rank : (unsigned)(KP_QN - 1) - qb_count - rank;
             KpRaw &Q = S.raw;
-            const unsigned packed = (unsigned)j0 | ((unsigned)k0 << 13) | ((unsigned)nx1 << 26) | ((unsigned)ny1 << 29);
+            // disjoint bit fields, written as a sum so that the compiler may fold shifts and adds into multiply-adds
+            const unsigned packed = (unsigned)j0 + (unsigned)k0 * 8192u + (unsigned)nx1 * 67108864u + (unsigned)ny1 * 536870912u;
             Q.a[idx] = make_float4(p.px0, p.py1, p.wpx, h);
             Q.b[idx] = make_float4(kp_get(b.W0, e), MODE == TSPLAT_MODE_DEPTH ? p.cz : kp_get(b.W1, e), kp_get(b.W2, e),
                                    __uint_as_float(packed));

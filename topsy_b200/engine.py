@@ -210,6 +210,16 @@ class SplatEngine:
         N.check(self.lib.tsplat_image_axpy(self._ctx, _ptr(dst), _ptr(src), ctypes.c_float(scale), dst.numel(),
                                            _stream(self.device)))
 
+    def enable_kernel_timing(self, enable: bool = True):
+        """Bracket every K1 launch with CUDA events (for the live roofline of bench.py)."""
+        N.check(self.lib.tsplat_enable_kernel_timing(self._ctx, int(bool(enable))))
+
+    def kernel_timing(self):
+        """(number of K1 launches, their summed duration in ms) since the last call; synchronises on those launches."""
+        n, ms = ctypes.c_int64(0), ctypes.c_double(0.0)
+        N.check(self.lib.tsplat_kernel_timing(self._ctx, ctypes.byref(n), ctypes.byref(ms)))
+        return n.value, ms.value
+
     def stats(self) -> dict:
         st = N.Stats()
         N.check(self.lib.tsplat_get_stats(self._ctx, ctypes.byref(st)))
