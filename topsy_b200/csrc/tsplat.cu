@@ -2,10 +2,10 @@
 // See include/tsplat.h for the boundary and DESIGN.md for the data layout / roofline of each kernel.
 //
 // Kernels
-//   K1  k_project_splat<MODE>   one pass over the SoA particle arrays (128-bit loads, 4 particles / thread):
-//                               rotate/project/cull, classify by projected footprint; footprints up to 8 px are splatted
-//                               immediately with vector REDs (REDG.E.ADD.F32{,x2,x4}) into the L2-resident image,
-//                               larger ones are appended to a 32-byte projected-record queue (one reservation per warp).
+//   K1  k_project_stream<MODE>  (tsplat_project.cuh) one pass over the SoA particle arrays as a per-warp software pipeline:
+//                               cp.async staging, rotate/project/cull, classify by projected footprint; footprints up to
+//                               8 px are compacted and splatted with vector REDs (REDG.E.ADD.F32{,x2,x4}) into the
+//                               L2-resident image, larger ones are appended to a 32-byte projected-record queue.
 //   K2  k_bin_count / k_bin_scan / k_bin_fill      counting sort of the queue by 64x32-pixel tile
 //   K3  k_tile_gather<MODE>     column strips in registers, LUT row addresses staged per (record, tile row),
 //                               whole kernel LUT in shared memory, no atomics in the loop
@@ -224,275 +224,6 @@ __device__ __forceinline__ float4 ld4_tail(const float *__restrict__ p, int64_t 
     if (left > 1) r.y = p[base + 1];
     if (left > 2) r.z = p[base + 2];
     return r;
-}
-
-// K1 works in two phases per warp so that the accumulation phase is divergence-free:
-//   phase A  every lane projects its 4 particles; small-footprint ones become 48-byte records in fixed slots of the
-//            warp's shared-memory slice.  ONE packed warp scan (cell counts | record counts) then gives every record its
-//            offset in the warp's flattened cell list and its rank among the non-empty records.
-//   phase B  the warp walks the flattened (particle, cell) list 32 entries at a time; a bit vector of segment heads +
-//            popc finds the owner record.  A cell is the group of CELL_W horizontally adjacent pixels that one 128-bit
-//            vector RED covers:  RGB 4 channels -> 1 pixel | WEIGHTED/DEPTH 2 channels -> 2 pixels | DENSITY -> 4 pixels
-constexpr int K1_THREADS = 128;
-constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_RECS = 128;                 // records per warp batch (4 per lane)
-constexpr int K1_MAX_SPAN = 8;               // direct particles cover at most 8 x 8 pixel centres
-constexpr int K1_BITWORDS = K1_RECS * K1_MAX_SPAN * (K1_MAX_SPAN / 2) / 32;     // work items: (cell column, row pair)
-
-struct __align__(16) DirectRec {
-    float px0, py1, inv, v0;
-    float v1, v2;
-    unsigned cjk;        // first cell column (low 16) | first row k0 (high 16)
-    unsigned offn;       // offset of the first work item in the warp's flattened list (bits 0-12) | cell columns - 1
-                         // (13-15) | rows - 1 (16-18)
-    unsigned jj;         // CELL_W > 1 only: first covered pixel column j0 (low 16) | last j1 (high 16)
-    unsigned pad[3];
-};
-
-template <int MODE, int CELL_W>
-__global__ void __launch_bounds__(K1_THREADS) k_project_splat(const ProjectArgs a)
-{
-    constexpr int CELL_SHIFT = CELL_W == 4 ? 2 : CELL_W == 2 ? 1 : 0;
-    // Warps are fully independent (no block-wide barrier): every warp stages its own copy of the 8x8 LUT level, and the
-    // loads that feed it are issued together with the particle loads so that one memory latency covers both.
-    __shared__ float s_lut8w[K1_WARPS][64];
-    // record of (e, lane) lives at byte e * (32 * 48 + 32) + lane * 48 of the warp's slice: the 32-byte skew between the
-    // four e-blocks puts the four records of one lane -- consecutive in the flattened list, so read together by
-    // neighbouring lanes in phase B -- into different bank groups (without it they are 1536 bytes apart: same banks)
-    constexpr int K1_REC_BLOCK = 32 * (int)sizeof(DirectRec) + 32;
-    __shared__ __align__(16) unsigned char s_rec_raw[K1_WARPS][4 * K1_REC_BLOCK];
-    __shared__ unsigned s_bits[K1_WARPS][K1_BITWORDS];
-    __shared__ unsigned char s_slot[K1_WARPS][K1_RECS];      // rank among non-empty records -> record slot
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    auto rec_at = [&](unsigned slot) -> DirectRec & {
-        return *reinterpret_cast<DirectRec *>(s_rec_raw[warp] + (slot >> 5) * K1_REC_BLOCK + (slot & 31u) * sizeof(DirectRec));
-    };
-    const float2 lut_pair = __ldg(reinterpret_cast<const float2 *>(a.lut + lut_offset(3)) + lane);
-    const uint64_t pol_stream = l2_policy_evict_first(), pol_image = l2_policy_evict_last();
-    const float *s_lut8 = s_lut8w[warp];
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t group = 0;
-    int e_first = 0, e_last = 0;                 // this lane's particles e in [e_first, e_last) are inside the range
-    const bool active = gi < a.n_groups;
-    if (active) {
-        int64_t lo, hi;
-        if (a.table.n > 0) {
-            int l = 0, r = a.table.n;            // invariant: gprefix[l] <= gi < gprefix[r]
-            while (r - l > 1) {
-                const int m = (l + r) >> 1;
-                if (a.table.gprefix[m] <= gi) l = m; else r = m;
-            }
-            lo = a.table.start[l];
-            hi = a.table.end[l];
-            group = (lo >> 2) + (gi - a.table.gprefix[l]);
-        } else {
-            lo = a.start; hi = a.end; group = a.g0 + gi;
-        }
-        const int64_t base = group << 2;
-        e_first = (int)max((int64_t)0, lo - base);
-        e_last = (int)min((int64_t)4, hi - base);
-    }
-
-    // ---- phase A: load, project, classify ---------------------------------------------------------------
-    float xs[4], ys[4], zs[4], hs[4], w0s[4], w1s[4], w2s[4];
-    {
-        float4 X, Y, Z, H, W0, W1, W2;
-        X = Y = Z = H = W0 = W1 = W2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int64_t base = group << 2;
-        if (active) {
-            if (base + 4 <= a.n_total) {
-                X = ld4(a.x, group, pol_stream); Y = ld4(a.y, group, pol_stream); Z = ld4(a.z, group, pol_stream); H = ld4(a.h, group, pol_stream); W0 = ld4(a.w0, group, pol_stream);
-                if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4(a.w1, group, pol_stream);
-                if (MODE == TSPLAT_MODE_RGB) W2 = ld4(a.w2, group, pol_stream);
-            } else {                              // partial last group of the buffer: element-wise, in bounds
-                const int64_t left = a.n_total - base;
-                X = ld4_tail(a.x, base, left); Y = ld4_tail(a.y, base, left); Z = ld4_tail(a.z, base, left);
-                H = ld4_tail(a.h, base, left); W0 = ld4_tail(a.w0, base, left);
-                if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) W1 = ld4_tail(a.w1, base, left);
-                if (MODE == TSPLAT_MODE_RGB) W2 = ld4_tail(a.w2, base, left);
-            }
-        }
-        xs[0] = X.x; xs[1] = X.y; xs[2] = X.z; xs[3] = X.w;   ys[0] = Y.x; ys[1] = Y.y; ys[2] = Y.z; ys[3] = Y.w;
-        zs[0] = Z.x; zs[1] = Z.y; zs[2] = Z.z; zs[3] = Z.w;   hs[0] = H.x; hs[1] = H.y; hs[2] = H.z; hs[3] = H.w;
-        w0s[0] = W0.x; w0s[1] = W0.y; w0s[2] = W0.z; w0s[3] = W0.w;
-        w1s[0] = W1.x; w1s[1] = W1.y; w1s[2] = W1.z; w1s[3] = W1.w;
-        w2s[0] = W2.x; w2s[1] = W2.y; w2s[2] = W2.z; w2s[3] = W2.w;
-    }
-
-    reinterpret_cast<float2 *>(s_lut8w[warp])[lane] = lut_pair;
-    unsigned n_culled = 0, n_direct = 0, n_deferred = 0;
-    unsigned cells4 = 0;                          // work items of the lane's 4 particles, 8 bits each (<= 32)
-    unsigned n_reds = 0;                          // cells = vector REDs of the lane's 4 particles
-    unsigned defer_mask = 0;                      // which of the lane's 4 particles go to the deferred queue
-    unsigned ncj4 = 0;                            // (cell columns - 1) | (rows - 1) << 3 of the lane's 4 direct particles, 8 bits each
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        if (e >= e_first && e < e_last) {
-            const Proj p = project(xs[e], ys[e], zs[e], hs[e], a.cam);
-            int j0, j1, k0, k1;
-            pixel_range(p.px0, p.px1, a.R, j0, j1);
-            pixel_range(p.py0, p.py1, a.R, k0, k1);
-            if (!p.keep) ++n_culled;
-            else if (j1 < j0 || k1 < k0) ++n_direct;          // no pixel centre covered (sub-pixel or off-screen)
-            else {
-                const float rhh = 1.0f / (hs[e] * hs[e]);
-                const float v0 = w0s[e] * rhh;
-                float v1, v2 = 0.0f;
-                if (MODE == TSPLAT_MODE_RGB) { v1 = w1s[e] * rhh; v2 = w2s[e] * rhh; }
-                else if (MODE == TSPLAT_MODE_DEPTH) v1 = p.cz;
-                else v1 = w1s[e];
-                if (p.wpx <= DIRECT_MAX_WPX && j1 - j0 < K1_MAX_SPAN && k1 - k0 < K1_MAX_SPAN) {
-                    ++n_direct;
-                    const int cj0 = j0 >> CELL_SHIFT;
-                    const unsigned ncj = (unsigned)((j1 >> CELL_SHIFT) - cj0 + 1);
-                    const unsigned nrows = (unsigned)(k1 - k0 + 1);
-                    cells4 |= (ncj * ((nrows + 1u) >> 1)) << (8 * e);          // work items: (cell column, row pair)
-                    n_reds += ncj * nrows;
-                    DirectRec &r = rec_at(e * 32 + lane);           // slot e*32+lane: conflict-free 128-bit stores
-                    *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.py1, 1.0f / p.wpx, v0);
-                    *reinterpret_cast<float4 *>(&r.v1) = make_float4(v1, v2, __uint_as_float((unsigned)cj0 | ((unsigned)k0 << 16)), 0.0f);
-                    if (CELL_W > 1) r.jj = (unsigned)j0 | ((unsigned)j1 << 16);
-                    ncj4 |= ((ncj - 1u) | ((nrows - 1u) << 3)) << (8 * e);
-                } else {
-                    // deferred: park the 32-byte queue record in the particle's own (otherwise unused) record slot;
-                    // it is copied to the global queue after ONE reservation per warp (below)
-                    ++n_deferred;
-                    defer_mask |= 1u << e;
-                    DirectRec &r = rec_at(e * 32 + lane);
-                    *reinterpret_cast<float4 *>(&r.px0) = make_float4(p.px0, p.px1, p.py0, p.py1);
-                    *reinterpret_cast<float4 *>(&r.v1) = make_float4(p.wpx, v0, v1, v2);
-                }
-            }
-        }
-    }
-
-    // one packed inclusive scan: bits 0-13 = cells (<= 8192), bits 14-22 = non-empty records (<= 128),
-    // bits 23-31 = deferred particles (<= 128)
-    const unsigned c0 = cells4 & 0xffu, c1 = (cells4 >> 8) & 0xffu, c2 = (cells4 >> 16) & 0xffu, c3 = cells4 >> 24;
-    const unsigned lane_cells = c0 + c1 + c2 + c3;
-    const unsigned lane_recs = (c0 != 0u) + (c1 != 0u) + (c2 != 0u) + (c3 != 0u);
-    const unsigned lane_defer = (unsigned)__popc(defer_mask);
-    unsigned incl = lane_cells | (lane_recs << 14) | (lane_defer << 23);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    // queue append: ONE global atomic per warp (same-address atomics serialise in the L2 at ~1 per ns, which bounds
-    // this kernel as soon as most particles are deferred), then every lane copies its parked records
-    if (total >> 23) {
-        unsigned qb = 0;
-        if (lane == 0) qb = atomicAdd(&a.counters->q_count, total >> 23);
-        qb = __shfl_sync(0xffffffffu, qb, 0);
-        unsigned slot = qb + (incl >> 23) - lane_defer;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (defer_mask & (1u << e)) {
-                if (slot < a.queue_cap) {
-                    const DirectRec &r = rec_at(e * 32 + lane);
-                    float4 *q = reinterpret_cast<float4 *>(a.queue + slot);
-                    q[0] = *reinterpret_cast<const float4 *>(&r.px0);
-                    q[1] = *reinterpret_cast<const float4 *>(&r.v1);
-                }
-                ++slot;
-            }
-        }
-    }
-    const unsigned T = total & 0x3fffu;
-    const unsigned n_words = (T + 31u) >> 5;
-    for (unsigned wi = lane; wi < n_words; wi += 32) s_bits[warp][wi] = 0u;
-    __syncwarp();
-    {
-        unsigned off = (incl & 0x3fffu) - lane_cells, rank = ((incl >> 14) & 0x1ffu) - lane_recs;
-        const unsigned cs[4] = {c0, c1, c2, c3};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (cs[e]) {
-                rec_at(e * 32 + lane).offn = off | (((ncj4 >> (8 * e)) & 63u) << 13);
-                s_slot[warp][rank] = (unsigned char)(e * 32 + lane);
-                atomicOr(&s_bits[warp][off >> 5], 1u << (off & 31u));
-                off += cs[e];
-                ++rank;
-            }
-        }
-    }
-    __syncwarp();
-
-    // ---- phase B: flattened (particle, cell) list ------------------------------------------------------------
-    unsigned rec_base = 0;
-    for (unsigned wi = 0; wi < n_words; ++wi) {
-        const unsigned word = s_bits[warp][wi];
-        const unsigned t = (wi << 5) + lane;
-        const unsigned rk = rec_base + __popc(word & (lt_mask | (1u << lane))) - 1u;
-        rec_base += __popc(word);
-        if (t < T) {
-            const DirectRec &r = rec_at(s_slot[warp][rk]);
-            const float4 ra = *reinterpret_cast<const float4 *>(&r.px0);      // px0 py1 inv v0
-            const float4 rb = *reinterpret_cast<const float4 *>(&r.v1);       // v1 v2 cjk off|ncj-1|rows-1
-            const unsigned cjk = __float_as_uint(rb.z), offn = __float_as_uint(rb.w);
-            const unsigned local = t - (offn & 0x1fffu), ncj = ((offn >> 13) & 7u) + 1u, nrows1 = (offn >> 16) & 7u;
-            // a work item is one cell column x two rows: the record is fetched once for two REDs, and neighbouring lanes
-            // still hold horizontally adjacent cells, which share sectors in the RED path
-            const unsigned dk2 = (unsigned)(local >= ncj) + (unsigned)(local >= 2u * ncj) + (unsigned)(local >= 3u * ncj);
-            const unsigned dc = local - dk2 * ncj;
-            const unsigned cj = (cjk & 0xffffu) + dc;
-            unsigned jj = 0;
-            if (CELL_W > 1) jj = r.jj;
-            auto emit = [&](const unsigned k) {
-                const float fy = (float)k + 0.5f;
-                const unsigned pix = k * (unsigned)a.R + cj * CELL_W;         // R <= 32768: fits 32 bits
-                if (CELL_W == 1) {
-                    const float K = sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)cj + 0.5f, fy);
-                    if (MODE == TSPLAT_MODE_RGB) {                       // RGB counts fragments even where K == 0
-                        red_v4(a.image + 4 * (size_t)pix, ra.w * K, rb.x * K, rb.y * K, 1.0f, pol_image);
-                    } else if (K != 0.0f) {                              // adding +0 is a no-op
-                        const float val = K * ra.w;
-                        if (MODE == TSPLAT_MODE_DENSITY) red_v1(a.image + pix, val, pol_image);
-                        else red_v2(a.image + 2 * (size_t)pix, val, val * rb.x, pol_image);
-                    }
-                } else {
-                    const unsigned j0 = jj & 0xffffu, j1 = jj >> 16;
-                    float Ks[CELL_W];
-                    bool any = false;
-#pragma unroll
-                    for (int c = 0; c < CELL_W; ++c) {
-                        const unsigned j = cj * CELL_W + c;
-                        const bool in = (j >= j0) && (j <= j1);
-                        Ks[c] = in ? sample_lut8(s_lut8, ra.z, ra.x, ra.y, (float)j + 0.5f, fy) : 0.0f;
-                        any |= (Ks[c] != 0.0f);
-                    }
-                    if (any) {
-                        if (MODE == TSPLAT_MODE_DENSITY) {
-                            red_v4(a.image + pix, Ks[0] * ra.w, Ks[1] * ra.w, Ks[2 % CELL_W] * ra.w, Ks[3 % CELL_W] * ra.w, pol_image);
-                        } else {                                  // two pixels x (val, val * q|cz)
-                            const float a0 = Ks[0] * ra.w, a1 = Ks[1] * ra.w;
-                            red_v4(a.image + 2 * (size_t)pix, a0, a0 * rb.x, a1, a1 * rb.x, pol_image);
-                        }
-                    }
-                }
-            };
-            const unsigned k = (cjk >> 16) + 2u * dk2;
-            emit(k);
-            if (2u * dk2 < nrows1) emit(k + 1u);
-        }
-    }
-
-    // warp-aggregated statistics: three global REDs per warp, spread over 32 counter slots to avoid same-address
-    // serialisation in the L2 (tsplat_get_stats sums the slots)
-    unsigned packed = n_culled | (n_direct << 8) | (n_deferred << 16);        // each <= 4 per lane, <= 128 per warp
-    for (int d = 16; d > 0; d >>= 1) packed += __shfl_down_sync(0xffffffffu, packed, d);
-    const unsigned warp_reds = __reduce_add_sync(0xffffffffu, n_reds);
-#ifndef TSPLAT_NO_STATS
-    if (lane == 0) {
-        StatSlot *slot = a.counters->slots + ((blockIdx.x * K1_WARPS + warp) & (STAT_SLOTS - 1));
-        const unsigned long long cd = (unsigned long long)(packed & 0xffu) | ((unsigned long long)((packed >> 8) & 0xffu) << 32);
-        if (cd) atomicAdd(&slot->culled_direct, cd);
-        if (warp_reds) atomicAdd(&slot->reds, (unsigned long long)warp_reds);   // cells = vector REDs issued (minus all-zero cells)
-        if (a.small_call && (packed >> 16)) atomicAdd(&a.counters->huge, (unsigned long long)(packed >> 16));
-    }
-#endif
 }
 
 #include "tsplat_project.cuh"
@@ -1746,9 +1477,8 @@ extern "C" int tsplat_set_scratch(tsplat_ctx *c, void *scratch, int64_t bytes)
 template <int MODE>
 static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups, const ScratchLayout &L, cudaStream_t st)
 {
-    const int threads = K1_THREADS;
-    const int64_t blocks = (n_groups + threads - 1) / threads;
-    if (blocks > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
+    const int64_t blocks = (n_groups + KP_THREADS - 1) / KP_THREADS;
+    if (n_groups > 0x7fffffffll) return set_err(TSPLAT_ERR_INVALID, "too many particles in one call");
     char *sc = static_cast<char *>(c->scratch);
     // per-call state: q_count .. pad, tile counters and cursors
     CUDA_TRY(cudaMemsetAsync(&c->d_counters->q_count, 0, (6 + PAIR_STRIPES) * sizeof(unsigned int), st));
@@ -1758,12 +1488,8 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
         constexpr int CW = ModeTraits<MODE>::C == 1 ? 4 : ModeTraits<MODE>::C == 2 ? 2 : 1;
         const bool timed = c->timing && c->timing_write - c->timing_read < TSPLAT_TIMING_SLOTS;
         if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->timing_write % TSPLAT_TIMING_SLOTS], st));
-        static const bool use_v1 = getenv("TSPLAT_K1_V1") != nullptr;       // round-1 kernel, kept for A/B timing only
-        if (use_v1) {
-            if (CW > 1 && (c->R % CW) == 0) k_project_splat<MODE, CW><<<(unsigned)blocks, threads, 0, st>>>(pa);
-            else k_project_splat<MODE, 1><<<(unsigned)blocks, threads, 0, st>>>(pa);
-        } else {
-            // persistent warps: one batch of 128 particles per warp and iteration, KP_CTAS_PER_SM resident CTAs per SM
+        {
+            // persistent warps: one batch of 128 particles per warp and iteration, as many CTAs as the SMs hold at once
             const int64_t n_batches = (n_groups + 31) >> 5;
             int64_t grid = (n_batches + KP_WARPS - 1) / KP_WARPS;
             if (CW > 1 && (c->R % CW) == 0) {
