@@ -72,7 +72,7 @@ struct Counters {
     unsigned int pair_total;     // nonzero once any (particle, tile) pair was reserved (this call)
     unsigned int work_counter;   // persistent-kernel work ticket
     unsigned int n_segments;     // gather work units (this call)
-    unsigned int pad;
+    unsigned int call_particles; // particles of this call (written by K1; read back with q_count as the next call's hint)
     unsigned int pair_sub[PAIR_STRIPES];   // pair-capacity reservations, striped: same-address atomics serialise in the L2
 };
 
@@ -113,6 +113,10 @@ struct tsplat_ctx {
     bool bin_attr_set;
     bool gather_attr_set[4];
     size_t bilateral_smem_set;   // largest dynamic shared-memory size k_bilateral_filter has been opted into
+    // length of the deferred queue after the previous render call of this context (read back asynchronously into pinned
+    // memory): a call whose predecessor deferred only a few records skips the four binning / gather launches and sends its
+    // own deferred records straight to the cooperative atomic kernel, which is correct for any number of records
+    unsigned *h_qhint;           // [0] = q_count, [5] = call_particles of the most recent call whose read-back has landed
     // optional live timing of K1 (tsplat_enable_kernel_timing): ring of event pairs, [timing_read, timing_write) pending
     bool timing;
     cudaEvent_t t_begin[TSPLAT_TIMING_SLOTS], t_end[TSPLAT_TIMING_SLOTS];
@@ -172,6 +176,7 @@ struct ProjectArgs {
     // single range (n_ranges == 1): particles [start, end); groups [g0, g0 + n_groups)
     int64_t start, end, g0, n_groups;
     int64_t n_total;             // particles in the buffers (the last 4-group may be partial)
+    unsigned call_particles;     // particles submitted by this call
     int small_call;              // the call is too small for the tile binning: deferred records all go to K3b
     RangeTable table;            // used when table.n > 0
 };
@@ -1330,6 +1335,8 @@ extern "C" int tsplat_create(int device_ordinal, int resolution, tsplat_ctx **ou
     CUDA_TRY(cudaMemset(c->d_counters, 0, sizeof(Counters)));
     CUDA_TRY(cudaMalloc(&c->d_select, sizeof(unsigned) * 4 * 2048));
     CUDA_TRY(cudaMallocHost(&c->h_select, sizeof(unsigned) * 4 * 2048));
+    CUDA_TRY(cudaMallocHost(&c->h_qhint, 6 * sizeof(unsigned)));
+    memset(c->h_qhint, 0, 6 * sizeof(unsigned));
     for (int s = 0; s < RANGE_SLOTS; ++s) {
         CUDA_TRY(cudaMallocHost(&c->h_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
         CUDA_TRY(cudaMalloc(&c->d_ranges[s], sizeof(int64_t) * (3 * (size_t)MAX_RANGES + 1)));
@@ -1349,6 +1356,7 @@ extern "C" int tsplat_destroy(tsplat_ctx *c)
     cudaFree(c->d_counters);
     cudaFree(c->d_select);
     cudaFreeHost(c->h_select);
+    cudaFreeHost(c->h_qhint);
     if (c->timing_events_created)
         for (int i = 0; i < TSPLAT_TIMING_SLOTS; ++i) { cudaEventDestroy(c->t_begin[i]); cudaEventDestroy(c->t_end[i]); }
     for (int s = 0; s < RANGE_SLOTS; ++s) {
@@ -1557,6 +1565,8 @@ static int launch_render(tsplat_ctx *c, const ProjectArgs &pa, int64_t n_groups,
         k_queue_atomic<MODE><<<c->sm_count * 8, 256, 0, st>>>(qa);
         c->launches += 5;
     }
+    if (pa.queue_cap > 0)       // q_count .. call_particles of this call -> pinned memory, for the next calls' routing hint
+        CUDA_TRY(cudaMemcpyAsync(c->h_qhint, &c->d_counters->q_count, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaGetLastError());
     return TSPLAT_OK;
 }
@@ -1640,6 +1650,15 @@ extern "C" int tsplat_render(tsplat_ctx *c, const int64_t *starts, const int64_t
         ProjectArgs a2 = args;
         a2.queue_cap = (unsigned)(chunk_cap < n_particles ? chunk_cap : n_particles);
         a2.small_call = a2.queue_cap < SMALL_QUEUE;
+        a2.call_particles = (unsigned)n_particles;
+        if (!a2.small_call && mode != TSPLAT_MODE_SURFACE) {
+            // hint only (K3b handles any queue length): deferred fraction of the most recent call whose read-back has
+            // landed x this call's particles.  The two words are read without synchronisation: a torn pair can only
+            // mis-steer one call between two correct paths.
+            const unsigned q_prev = reinterpret_cast<volatile unsigned *>(c->h_qhint)[0];
+            const unsigned n_prev = reinterpret_cast<volatile unsigned *>(c->h_qhint)[5];
+            if (n_prev > 0) a2.small_call = (double)q_prev / (double)n_prev * (double)n_particles < SMALL_QUEUE / 2;
+        }
         a2.n_groups = n_groups;
         switch (mode) {
         case TSPLAT_MODE_SURFACE: return launch_render_surface(c, a2, n_groups, st);

@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(KP_THREADS, 5) k_project_stream(const ProjectA
     KpWarpSmem &S = s_warp[warp];
     KpStage &stage = s_stage[warp];
     if (threadIdx.x < 64) s_lut8[threadIdx.x] = __ldg(a.lut + lut_offset(3) + threadIdx.x);
+    if (blockIdx.x == 0 && threadIdx.x == 64) a.counters->call_particles = a.call_particles;
     for (int i = lane; i < KP_BWN; i += 32) S.bits[i] = 0u;
     __syncthreads();                              // the only block-wide barrier: warps are independent from here on
     const uint64_t pol_stream = l2_policy_evict_first(), pol_image = l2_policy_evict_last();
