@@ -87,7 +87,7 @@ def visualizer_check(rank, world):
         rp = v._sph._render_progression
         rp._recommended_num_particles_to_render = per_frame
         rp._perform_particle_number_update = lambda: None
-        v._sph._render_timer.total_time_in_frame = lambda: 1.0
+        v._sph._render_timer.total_time_in_frame = lambda wait=True: 1.0
         v.render_sph(DrawReason.CHANGE)
         frames = 1
         while v._sph.needs_refine() and frames < 100:     # collective when sharded: true until the slowest rank is done

@@ -153,7 +153,7 @@ def test_progressive_refine_converges_to_export():
             return self
         def __exit__(self, *exc):
             self.t += 1.0 / 30
-        def total_time_in_frame(self):
+        def total_time_in_frame(self, wait=True):
             return self.t
         def end_frame(self):
             self.t = 0.0

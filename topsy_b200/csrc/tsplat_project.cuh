@@ -85,14 +85,16 @@ __device__ __forceinline__ unsigned kp_issue(const ProjectArgs &a, unsigned gi, 
             // single range [start, end): only its first and last group can be partial
             group = (unsigned)a.g0 + gi;
             mask = 0xfu;
-            if (gi == 0u) mask &= ~((1u << (unsigned)(a.start & 3)) - 1u);
-            if (gi == (unsigned)a.n_groups - 1u) mask &= (2u << (unsigned)((a.end - 1) & 3)) - 1u;
+            if (gi - 1u >= (unsigned)a.n_groups - 2u) {      // gi == 0 or gi == n_groups - 1 (one compare, rarely taken)
+                if (gi == 0u) mask &= ~((1u << (unsigned)(a.start & 3)) - 1u);
+                if (gi == (unsigned)a.n_groups - 1u) mask &= (2u << (unsigned)((a.end - 1) & 3)) - 1u;
+            }
         }
         const float4 *px = reinterpret_cast<const float4 *>(a.x) + group, *py = reinterpret_cast<const float4 *>(a.y) + group;
         const float4 *pz = reinterpret_cast<const float4 *>(a.z) + group, *ph = reinterpret_cast<const float4 *>(a.h) + group;
         const float4 *p0 = reinterpret_cast<const float4 *>(a.w0) + group, *p1 = reinterpret_cast<const float4 *>(a.w1) + group;
         const float4 *p2 = reinterpret_cast<const float4 *>(a.w2) + group;
-        if ((int64_t)group * 4 + 4 <= a.n_total) {
+        if (group < (unsigned)(a.n_total >> 2)) {      // the group lies wholly inside the buffers (n_total < 2^33 per call)
             kp_cp_async16(&st.v[0][lane], px, pol); kp_cp_async16(&st.v[1][lane], py, pol); kp_cp_async16(&st.v[2][lane], pz, pol);
             kp_cp_async16(&st.v[3][lane], ph, pol); kp_cp_async16(&st.v[4][lane], p0, pol);
             if (MODE == TSPLAT_MODE_WEIGHTED || MODE == TSPLAT_MODE_RGB) kp_cp_async16(&st.v[5][lane], p1, pol);

@@ -78,6 +78,11 @@ class RenderProgression:
         self._total_num_rendered_in_frame += self._last_num_to_render
         self._time_in_frame = time_elapsed_in_frame
 
+    def set_time_in_frame(self, time_elapsed_in_frame: float):
+        """The frame's device time, when it was not known yet at the last ``end_block`` (EXPORT frames are not
+        synchronised block by block); feeds the particle-budget update of ``end_frame_get_scalefactor``."""
+        self._time_in_frame = time_elapsed_in_frame
+
     def end_frame_get_scalefactor(self):
         """Close the frame, adapt the particle budget, return N / particles accumulated so far."""
         self._perform_particle_number_update()

@@ -149,12 +149,17 @@ class SPH:
         buffers.specify_vertex_buffer_assignment(['pos_smooth', self._buffer_name])
 
         clear = self._render_progression.start_frame(draw_reason)
-        while block := self._render_progression.get_block(self._render_timer.total_time_in_frame()):
+        # an EXPORT frame's block sizes do not depend on the elapsed time (progressive_render.py:67-70): its blocks are
+        # enqueued back to back and the host waits once, when the frame's time is handed to the progression below
+        wait = draw_reason != DrawReason.EXPORT
+        while block := self._render_progression.get_block(self._render_timer.total_time_in_frame(wait)):
             buffers.update_particle_ranges(*block)
             with self._render_timer:
                 buffers.issue_draw(self._engine, mode, clear, image=image)
-            self._render_progression.end_block(self._render_timer.total_time_in_frame())
+            self._render_progression.end_block(self._render_timer.total_time_in_frame(wait))
             clear = False
+        if not wait:
+            self._render_progression.set_time_in_frame(self._render_timer.total_time_in_frame())
         self._render_timer.end_frame()
 
         self.last_render_mass_scale = self._render_progression.end_frame_get_scalefactor()
