@@ -109,6 +109,23 @@ def test_mag_parameters(device):
     assert h['vmin'] == pytest.approx(o.mag_per_arcsec2_to_log_output(25.0))
 
 
+def test_mag_parameters_known_answers(device):
+    """The reference's own known answers for the vmin/vmax <-> magnitude conversion
+    (/root/reference/tests/test_colormap.py:88-104), in both directions through the holder."""
+    img = np.ones((8, 8, 4), np.float32)
+    h, _ = holder_for(device, img, {'type': 'rgb', 'hdr': False, 'log': True})
+    h.update_parameters({'vmin': 1.0, 'vmax': 2.0})
+    assert h.get_parameter('vmin') == 1.0 and h.get_parameter('vmax') == 2.0
+    assert np.allclose(h.get_parameter('min_mag'), 31.57212566586528)
+    assert np.allclose(h.get_parameter('max_mag'), 34.07212566586528)
+    h.update_parameters({'min_mag': 1.0, 'max_mag': 2.0})
+    assert np.allclose(h.get_parameter('min_mag'), 1.0) and np.allclose(h.get_parameter('max_mag'), 2.0)
+    assert np.allclose(h.get_parameter('vmin'), 13.828850266346112)
+    assert np.allclose(h.get_parameter('vmax'), 14.228850266346113)
+    h['vmin'] = 5.0                                   # dictionary access (:107-117)
+    assert h['vmin'] == 5.0 and h['type'] == 'rgb'
+
+
 def test_holder_dispatch_and_host_roundtrip(device):
     img = make_image(R=32)
     h, _ = holder_for(device, img, {'type': 'density', 'colormap_name': 'viridis'})

@@ -66,6 +66,14 @@ def test_rgb_hdr_golden(fx, goldens, oracle_lut):
     np.testing.assert_allclose(out[::20, ::20].ravel().astype(np.float64), goldens["test_hdr_rgb_render__result_ref"], atol=1e-2)
 
 
+def test_magnitude_conversion_known_answers():
+    # reference tests/test_colormap.py:88-104: vmin/vmax 1, 2 <-> max_mag/min_mag 34.07.., 31.57..; mags 1, 2 <-> 14.22.., 13.82..
+    assert np.isclose(o.mag_per_arcsec2_to_log_output(31.57212566586528), 2.0)
+    assert np.isclose(o.mag_per_arcsec2_to_log_output(34.07212566586528), 1.0)
+    assert np.isclose(o.mag_per_arcsec2_to_log_output(2.0), 13.828850266346112)
+    assert np.isclose(o.mag_per_arcsec2_to_log_output(1.0), 14.228850266346113)
+
+
 def test_depth_golden(fx, goldens, oracle_lut):
     # reference :302-343
     rot = np.array([[1.0, 0, 0], [0, 0, 1.0], [0, -1.0, 0]])

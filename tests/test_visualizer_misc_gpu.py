@@ -41,6 +41,29 @@ def test_split_buffers_give_the_same_image(monkeypatch):
     assert many._sph._engine.stats()["particles_submitted"] <= 5000
 
 
+def test_create_and_write_split_buffers():
+    """Mirrors the reference's test_create_buffers / test_write_buffers (/root/reference/tests/test_split_buffers.py:68-93):
+    one device buffer per physical buffer, sized by its particle count; writes are checked for buffer and particle counts
+    and land in the right slices."""
+    from topsy_b200.device import Device
+    from topsy_b200.split_buffers import SplitBuffers
+    device = Device()
+    sb = SplitBuffers(50, 15)
+    buffers = sb.create_buffers(device, 4)
+    assert len(buffers) == 4
+    assert all(buf.numel() * buf.element_size() == 15 * 4 for buf in buffers[:-1])
+    assert buffers[-1].numel() * buffers[-1].element_size() == 5 * 4
+    data = np.arange(50, dtype=np.float32)
+    with pytest.raises(ValueError):
+        sb.write_buffers(device, buffers[:-1], data)        # wrong number of buffers
+    with pytest.raises(ValueError):
+        sb.write_buffers(device, buffers, data[:-1])        # wrong number of particles
+    sb.write_buffers(device, buffers, data)
+    for k, buf in enumerate(buffers):
+        first, last = sb.buffer_range(k)
+        npt.assert_array_equal(buf.cpu().numpy().view(np.float32), data[first:last])
+
+
 def test_canvas_interaction():
     vis = topsy.test(2000, render_resolution=100, canvas_class=offscreen.VisualizerCanvas)
     vis.scale = 50.0
