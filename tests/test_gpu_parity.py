@@ -162,6 +162,73 @@ def test_uniform_box_parity(oracle_lut, mode, R, n, hscale):
         eng.close()
 
 
+# Seeded sweep over what the fixed cases above keep constant: resolutions that are not multiples of the 128-bit cell width
+# (density / weighted fall back to one-pixel cells), views that cut the particle cloud, offsets, signed second weights,
+# ragged ranges, every footprint regime from sub-pixel to bilinear in one image, and every mode.
+@pytest.mark.parametrize("seed,mode,R,n,px_med", [
+    (0, o.MODE_DENSITY, 50, 3000, 0.6), (1, o.MODE_WEIGHTED, 97, 20000, 2.5), (2, o.MODE_RGB, 201, 50000, 1.2),
+    (3, o.MODE_DEPTH, 333, 40000, 4.0), (4, o.MODE_DENSITY, 201, 250000, 12.0), (5, o.MODE_WEIGHTED, 333, 220000, 9.0),
+    (6, o.MODE_RGB, 97, 180000, 14.0), (7, o.MODE_DEPTH, 201, 200000, 30.0), (8, o.MODE_DENSITY, 1000, 300000, 0.3),
+    (9, o.MODE_WEIGHTED, 640, 1, 40.0), (10, o.MODE_RGB, 512, 37, 90.0), (11, o.MODE_DENSITY, 333, 150000, 70.0)])
+def test_seeded_configuration_sweep(oracle_lut, seed, mode, R, n, px_med):
+    from topsy_b200.engine import SplatEngine
+    rs = np.random.RandomState(4200 + seed)
+    scale = float(10 ** rs.uniform(-0.3, 1.3))
+    pos = (rs.normal(size=(n, 3)) * scale * rs.uniform(0.4, 1.6)).astype(np.float32)      # part of the cloud is out of view
+    h = (px_med * scale / (2.0 * R) * np.exp(rs.normal(size=n) * 0.8)).astype(np.float32)  # wpx = 2 h R / scale
+    m = rs.uniform(0.1, 1.0, n).astype(np.float32)
+    w = {o.MODE_DENSITY: (m,), o.MODE_DEPTH: (m,), o.MODE_WEIGHTED: (m, rs.normal(size=n).astype(np.float32)),
+         o.MODE_RGB: (m, rs.uniform(0, 1, n).astype(np.float32), rs.uniform(0, 2, n).astype(np.float32))}[mode]
+    rot = o.rotate(np.eye(3), rs.uniform(-3, 3), rs.uniform(-1.5, 1.5))
+    M = o.transform_matrix(rot, rs.normal(size=3) * 0.2 * scale, scale); sf = o.scale_factor(scale)
+    ranges = None
+    if seed % 3 == 1 and n > 100:                       # ragged, unaligned ranges with gaps
+        cuts = np.sort(rs.choice(n, size=8, replace=False))
+        starts = cuts[::2].astype(np.int64); lens = (cuts[1::2] - cuts[::2]).astype(np.int64)
+        ranges = (starts, lens)
+    ref, mag = oracle_pair(pos[:, 0], pos[:, 1], pos[:, 2], h, w, M, sf, R, mode, oracle_lut, ranges=ranges)
+    eng = SplatEngine(R)
+    try:
+        eng.set_kernel_lut(oracle_lut)
+        eng.set_camera(M, sf)
+        x, y, z, hd = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], h)
+        eng.set_particles(x, y, z, hd); eng.set_weights(*_to_dev(*w))
+        img = (eng.render(mode) if ranges is None else eng.render(mode, ranges[0], ranges[1])).cpu().numpy()
+        assert_image_parity(img, ref, f"sweep seed {seed} mode {mode} R {R}", mag)
+        want = n if ranges is None else int(ranges[1].sum())
+        assert eng.stats()["particles_submitted"] == want
+    finally:
+        eng.close()
+
+
+def test_image_wider_than_the_direct_path_packs(oracle_lut):
+    """R > 8192: K1 packs pixel coordinates into 13 bits, so on larger images every covered particle takes the deferred
+    route (tsplat_project.cuh, KP_MAX_R).  Few particles, one oracle thread: the fp64 reference image is 0.5 GB."""
+    from topsy_b200.engine import SplatEngine
+    R, n = 8200, 3000
+    rs = np.random.RandomState(77)
+    pos = rs.uniform(-1, 1, (n, 3)).astype(np.float32)
+    h = (np.array([0.3, 2.0, 9.0, 40.0])[rs.randint(4, size=n)] / (2.0 * R) * np.exp(rs.normal(size=n) * 0.3)).astype(np.float32)
+    m = rs.uniform(0.1, 1.0, n).astype(np.float32)
+    M = o.transform_matrix(np.eye(3), np.zeros(3), 1.0); sf = o.scale_factor(1.0)
+    ref = co.splat(pos[:, 0], pos[:, 1], pos[:, 2], h, (m,), M, sf, R, o.MODE_DENSITY, oracle_lut, nthreads=1)
+    eng = SplatEngine(R, max_particles_per_call=1 << 16)
+    try:
+        eng.set_kernel_lut(oracle_lut)
+        eng.set_camera(M, sf)
+        x, y, z, hd, md = _to_dev(pos[:, 0], pos[:, 1], pos[:, 2], h, m)
+        eng.set_particles(x, y, z, hd); eng.set_weights(md)
+        img = eng.render(o.MODE_DENSITY).cpu().numpy()[..., 0].astype(np.float64)
+        st = eng.stats()
+    finally:
+        eng.close()
+    ref = ref[..., 0]
+    assert st["direct_vector_reds"] == 0 and st["particles_huge"] > 0, st       # nothing was splatted by K1 itself
+    big = ref > FLOOR * ref.max()
+    assert (np.abs(img[big] - ref[big]) / ref[big]).max() <= REL_TOL
+    assert np.abs(img[~big] - ref[~big]).max() <= 2 * FLOOR * ref.max()
+
+
 def test_pair_capacity_overflow_falls_back_to_atomics(oracle_lut):
     """250k footprints that each cover all 32 gather tiles of a 256^2 image: 8M (record, tile) pairs against a capacity of
     6 per queue slot (striped over 32 reservation counters) -> part of the records must take the cooperative atomic path,
