@@ -445,9 +445,14 @@ def run_ours(args):
         k_ms = torch.tensor([sharded.kernel_events[0].elapsed_time(sharded.kernel_events[1])], device=dev, dtype=torch.float64)
         dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
         sharded.kernel_events = None
-        link_bytes = (world - 1) / world * R * R * C * 4
-        reduce_kernel = {"kernel": "k_reduce_colormap", "ms_max_over_ranks": float(k_ms[0]), "nvlink_bytes_in_per_rank": link_bytes,
-                         "nvlink_GBs_in_per_rank": link_bytes / (float(k_ms[0]) * 1e-3) / 1e9,
+        # NVLink bytes INTO each rank: its slab of every other rank's partial image; rank 0 also receives everybody else's
+        # RGBA8 rows (the slabs are sized so that the two kinds of rank pull the same amount, distributed.presentation_slab)
+        from topsy_b200.distributed import presentation_slab
+        rows = [presentation_slab(R, r, world, 4 * C, 4)[1] for r in range(world)]
+        bytes_in = [(world - 1) * rows[r] * R * C * 4 + ((R - rows[0]) * R * 4 if r == 0 else 0) for r in range(world)]
+        link_bytes = float(max(bytes_in))
+        reduce_kernel = {"kernel": "k_reduce_colormap", "ms_max_over_ranks": float(k_ms[0]), "rows_per_rank": rows,
+                         "nvlink_bytes_in_per_rank": bytes_in, "nvlink_GBs_in_busiest_rank": link_bytes / (float(k_ms[0]) * 1e-3) / 1e9,
                          "frac_of_measured_peer_copy_770GBs": link_bytes / (float(k_ms[0]) * 1e-3) / 1e9 / 770.0}
 
     sampler = ClockSampler(local_rank)

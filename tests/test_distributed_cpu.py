@@ -53,6 +53,33 @@ def test_shards_keep_cell_structure_for_the_progression():
         assert (hits == 1).all()
 
 
+def test_presentation_slabs_tile_the_image_and_balance_the_link_cost():
+    """The slabs of the fused reduce + colormap kernel: contiguous, cover every row once, and sized so that the gather
+    destination (which also receives everybody's RGBA rows) is busy no longer than the other ranks."""
+    k = D.REMOTE_STORE_COST
+    for R in (200, 2048, 4097):
+        for world in (1, 2, 3, 8):
+            for in_b, out_b in ((4, 4), (8, 4), (16, 4), (16, 16), (4, 16)):
+                slabs = [D.presentation_slab(R, r, world, in_b, out_b) for r in range(world)]
+                assert slabs[0][0] == 0 and sum(n for _, n in slabs) == R
+                for (a, n), (b, _) in zip(slabs, slabs[1:]):
+                    assert a + n == b
+                if world == 1:
+                    continue
+                rows = [n for _, n in slabs]
+
+                def slowest(rows_dst, rows_other):      # link work of the busiest rank, in units of loaded bytes
+                    return max((world - 1) * rows_dst * R * in_b + k * (R - rows_dst) * R * out_b,
+                               rows_other * R * ((world - 1) * in_b + k * out_b))
+
+                got = slowest(rows[0], max(rows[1:]))
+                assert got <= slowest(-(-R // world), -(-R // world)) * (1 + 1e-12)          # never worse than equal slabs
+                for n_dst in range(0, R + 1, max(1, R // 64)):                               # ... or than any other split
+                    assert got <= slowest(n_dst, -(-(R - n_dst) // (world - 1))) * (1 + 1e-12)
+    assert abs(D.presentation_slab(4096, 0, 2, 4, 4)[1] - 2048) <= 1     # two GPUs: equal slabs
+    assert 250 < D.presentation_slab(4096, 0, 8, 4, 4)[1] < 350          # c5 on 8 GPUs: ~7 % of the rows instead of 12.5 %
+
+
 def test_row_slabs_tile_the_image():
     for R in (200, 2048, 4097):
         for world in (1, 2, 3, 8):

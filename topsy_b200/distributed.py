@@ -51,6 +51,38 @@ def row_slab(resolution: int, rank: int, world: int):
     return row0, base + (1 if rank < extra else 0)
 
 
+# NVLink cost of a byte of RGBA that a rank stores into (or receives from) a peer, relative to a byte of partial image it
+# LOADS from a peer: loads are round trips, stores are posted.  Measured with the fused kernel on 2 x B200: a rank that
+# only loads 67 MB takes 0.149 ms (452 GB/s); with equal slabs (33.5 MB loaded per rank, 33.5 MB of RGBA crossing once)
+# both ranks take 0.113 ms, i.e. a stored byte costs its sender and its receiver ~0.53 of a loaded byte.
+REMOTE_STORE_COST = 0.53
+
+
+def presentation_slab(resolution: int, rank: int, world: int, in_bytes_per_pixel: int, out_bytes_per_pixel: int,
+                      dst: int = 0):
+    """Rows of the image that ``rank`` reduces and colormaps when the RGBA result is gathered on rank ``dst``.
+
+    What bounds the fused kernel is each GPU's NVLink work.  A rank that owns n rows loads them from the other world - 1
+    partial images and (unless it is ``dst``) stores n rows of RGBA to ``dst``; ``dst`` receives the RGBA rows of
+    everybody else.  With equal slabs ``dst`` is the straggler on more than two GPUs (c5 on 8 GPUs: 59 MB loaded and 59 MB
+    received, 0.195 ms, against 59 MB + 8 MB sent for the others); its slab is chosen so that the slowest rank is as fast
+    as possible (two GPUs: equal slabs; c5 on 8: 7 % of the rows instead of 12.5 %)."""
+    if world == 1:
+        return 0, resolution
+    i_b, o_b = float(in_bytes_per_pixel), REMOTE_STORE_COST * float(out_bytes_per_pixel)
+    # exact over the integer row counts (covers the corner where the output is larger than a partial image, too)
+    n = np.arange(resolution + 1, dtype=np.float64)
+    cost_dst = (world - 1) * n * i_b + (resolution - n) * o_b
+    cost_others = np.ceil((resolution - n) / (world - 1)) * ((world - 1) * i_b + o_b)
+    n_dst = int(np.argmin(np.maximum(cost_dst, cost_others)))
+    others = [r for r in range(world) if r != dst]
+    base, extra = divmod(resolution - n_dst, world - 1)
+    rows = {r: base + (1 if k < extra else 0) for k, r in enumerate(others)}
+    rows[dst] = n_dst
+    row0 = sum(rows[r] for r in range(rank))
+    return row0, rows[rank]
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # sharding of the drop-in classes (Visualizer / loaders / SPH) under torchrun
 # ----------------------------------------------------------------------------------------------------------------
@@ -205,6 +237,7 @@ class ShardedSplat:
         fmt, tdtype = {"rgba8unorm": (N.FMT_RGBA8, torch.uint8), "rgba16float": (N.FMT_RGBA16F, torch.float16),
                        "rgba32float": (N.FMT_RGBA32F, torch.float32)}[out_format]
         self._fmt = fmt
+        self._out_pixel_bytes = {N.FMT_RGBA8: 4, N.FMT_RGBA16F: 8, N.FMT_RGBA32F: 16}[fmt]
         self.method = reduce
         if reduce == "auto":
             self.method = "p2p" if self.world > 1 else "local"
@@ -251,7 +284,7 @@ class ShardedSplat:
             self._hdl.barrier()                                   # every rank's partial image is complete and visible
             if self.kernel_events is not None:
                 self.kernel_events[0].record()
-            row0, nrows = row_slab(self.resolution, self.rank, self.world)
+            row0, nrows = presentation_slab(self.resolution, self.rank, self.world, 4 * self.channels, self._out_pixel_bytes)
             lw, lh = (0, 0) if lut is None else ((lut.shape[0], 1) if lut.dim() == 2 else (lut.shape[1], lut.shape[0]))
             stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             N.check(eng.lib.tsplat_reduce_colormap(eng._ctx, self._peer_ptrs, self.world, self.channels, row0, nrows,
