@@ -165,3 +165,31 @@ def test_shard_loader_stripes_partition_the_snapshot(world):
     np.testing.assert_array_equal(t1.get_positions(), t0.get_positions()[1::world])
     np.testing.assert_array_equal(t1.get_smooth(), t0.get_smooth()[1::world])
     assert len(t1.get_mass()) == len(t1) == len(range(1, 1000, world))
+
+
+@pytest.mark.parametrize("world,n_total", [(2, 100_003), (3, 50_000), (8, 9_000)])
+def test_synthetic_stripes_are_slices_of_one_snapshot(world, n_total):
+    """bench.py's N > 1 parity check rests on this: rank r of G generates exactly the particles that per-cell striping
+    (shard_indices) picks from the single-GPU snapshot, bit for bit, and that snapshot is already in topsy's cell order.
+    Also covers stripes with empty cells (9000 particles over 4096 cells and 8 ranks)."""
+    torch = pytest.importorskip("torch")
+    from topsy_b200 import synthetic
+    wl = synthetic.WORKLOADS["c3"]                                       # weighted: x y z h m q
+    full, lengths = synthetic.generate_striped(wl, "cpu", n_total=n_total, chunk=7001)
+    assert int(lengths.sum()) == n_total
+    offsets = np.cumsum(lengths.numpy()) - lengths.numpy()
+    seen = 0
+    for rank in range(world):
+        part, mine = synthetic.generate_striped(wl, "cpu", n_total=n_total, rank=rank, world=world, chunk=4999)
+        idx = D.shard_indices(offsets, lengths.numpy(), rank, world)
+        assert np.array_equal(mine.numpy(), D.shard_cell_lengths(lengths.numpy(), rank, world))
+        assert synthetic.stripe_size(n_total, rank, world) == len(idx)
+        for name, arr in part.items():
+            assert torch.equal(arr, full[name][torch.from_numpy(idx)]), (rank, name)
+        seen += len(idx)
+    assert seen == n_total
+    # the snapshot is in cell order: the reference's cell layout of it is the identity permutation
+    pos = np.stack([full[k].numpy() for k in "xyz"], axis=1)
+    layout, ordering = CellLayout.from_positions(pos, -0.5 * synthetic.BOX, 0.5 * synthetic.BOX, synthetic.NSIDE)
+    assert np.array_equal(ordering, np.arange(n_total))
+    assert np.array_equal(layout._lengths, lengths.numpy())
