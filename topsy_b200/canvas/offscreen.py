@@ -5,8 +5,6 @@ handler registry, ``request_draw`` coalescing, a context that hands out a target
 ``draw()`` which runs the pending draw function and returns the frame as a numpy array."""
 from __future__ import annotations
 
-import numpy as np
-
 from . import VisualizerCanvasBase
 
 _PRESENT_FORMATS = {"rgba8unorm": "rgba-u8", "bgra8unorm": "bgra-u8", "rgba16float": "rgba-f16"}

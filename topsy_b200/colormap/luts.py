@@ -10,7 +10,6 @@ The GPU colormap kernel takes any (N,4) / (N,N,4) float32 table, so user-supplie
 """
 from __future__ import annotations
 
-import colorsys
 import logging
 
 import numpy as np
